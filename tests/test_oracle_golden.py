@@ -1,0 +1,156 @@
+"""Pins the numpy oracle against vectors produced by the REAL reference
+(tests/golden/make_golden.py) and the reference's only numeric fixture
+(docs/ray_data.tsv)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def weights(npz):
+    return {k[2:]: npz[k] for k in npz.files if k.startswith("w.")}
+
+
+def test_torch_linspace_bit_exact():
+    g = load("sampler.npz")
+    for n in (64, 63, 7):
+        assert np.array_equal(oracle.torch_linspace(0, 1, n), g["linspace_%d" % n])
+
+
+def test_raycast_and_near_far():
+    g = load("sampler.npz")
+    o, d = oracle.raycast(g["intrinsics"][1], g["extrinsics"][1], g["points"])
+    np.testing.assert_allclose(o, g["cam1_starts"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(d, g["cam1_dirs"], rtol=0, atol=2e-6)
+    nf, valid = oracle.near_far(g["bounds"], g["starts"], g["directions"])
+    assert np.array_equal(np.nonzero(~valid)[0], g["invalid"])
+    assert np.array_equal(nf[:, valid], g["near_far"][:, valid])
+
+
+def test_sample_stratified_bit_exact():
+    g = load("sampler.npz")
+    idx = g["idx"]
+    near, far = g["near_far"][:, idx]
+    s = oracle.sample_rays(g["starts"][idx], g["directions"][idx], near, far, 64, u=g["u"])
+    assert np.array_equal(s.t_values, g["t_values"])
+    assert np.array_equal(s.positions, g["positions"])
+    assert np.array_equal(s.view_directions, g["view_directions"])
+    s = oracle.sample_rays(g["starts"][idx], g["directions"][idx], near, far, 64, u=None)
+    assert np.array_equal(s.t_values, g["t_uniform"])
+
+
+def test_sample_anneal_bit_exact():
+    g = load("sampler.npz")
+    idx = g["idx"]
+    near, far = g["near_far"][:, idx]
+    s = oracle.sample_rays(g["starts"][idx], g["directions"][idx], near, far, 64,
+                           u=g["u_anneal"], step=500, num_anneal_steps=2000, anneal_start=0.2)
+    assert np.array_equal(s.t_values, g["t_anneal"])
+    assert np.array_equal(s.positions, g["pos_anneal"])
+
+
+def test_blend_weights():
+    g = load("blend.npz")
+    w = oracle.calculate_blend_weights(g["t"], g["sigma"])
+    # exp() differs by 1 ulp between numpy and ATen; 1-alpha amplifies it where alpha~1
+    np.testing.assert_allclose(w, g["w"], rtol=2e-6, atol=1.2e-7)
+
+
+def test_ray_data_tsv_known_answer():
+    """docs/ray_data.tsv: T column == inclusive transmittance."""
+    g = load("ray_data_kat.npz")
+    t, sig, T = g["t"][None], g["opacity"][None], g["T"]
+    deltas = np.concatenate([t[:, 1:] - t[:, :-1], np.full((1, 1), 1e10, np.float32)], -1)
+    alpha = 1 - np.exp(-(sig * deltas))
+    w = oracle.calculate_blend_weights(t, sig)[0]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        trans_excl = np.where(alpha[0] > 1e-20, w / alpha[0], np.nan)
+    ok = ~np.isnan(trans_excl[1:])
+    # exclusive transmittance at i+1 == inclusive (TSV) at i; the TSV holds 3-8 printed digits
+    np.testing.assert_allclose(trans_excl[1:][ok], T[:-1][ok], rtol=2e-3, atol=2e-5)
+
+
+def test_nerf_forward_and_render():
+    g = load("nerf_render.npz")
+    p = weights(g)
+    raw = oracle.nerf_forward(p, g["positions"].reshape(-1, 3), g["view_directions"].reshape(-1, 3))
+    # fp32 GEMM summation order differs between MKL (reference) and numpy's BLAS
+    err = np.abs(raw - g["raw"]).max()
+    scale = np.abs(g["raw"]).max()
+    assert err <= 2e-5 * max(1.0, scale), (err, scale)
+    out = oracle.render(raw.reshape(192, 64, 4), g["t_values"], True)
+    np.testing.assert_allclose(out.color, g["color"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(out.alpha, g["alpha"], rtol=0, atol=2e-5)
+    assert (out.depth != g["depth"]).mean() <= 0.01
+    # with the reference's own raw outputs the compositing is near bit-exact
+    out = oracle.render(g["raw"].reshape(192, 64, 4), g["t_values"], True)
+    np.testing.assert_allclose(out.color, g["color"], rtol=0, atol=5e-7)
+    np.testing.assert_allclose(out.alpha, g["alpha"], rtol=0, atol=5e-7)
+    assert np.array_equal(out.depth, g["depth"])
+
+
+def test_nerf_forward_fp64_arbiter():
+    g = load("nerf_render.npz")
+    p = {k: v.astype(np.float64) for k, v in weights(g).items()}
+    raw = oracle.nerf_forward(p, g["positions"].reshape(-1, 3).astype(np.float64),
+                              g["view_directions"].reshape(-1, 3).astype(np.float64))
+    np.testing.assert_allclose(raw, g["raw64"], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["mlp", "basic", "positional", "gaussian"])
+def test_ffmlp_presets(name):
+    g = load("ffmlp_%s.npz" % name)
+    p = weights(g)
+    a = p.pop("a_values", None)
+    b = p.pop("b_values", None)
+    raw = oracle.ffmlp_forward(p, g["positions"].reshape(-1, 3), a, b)
+    err = np.abs(raw - g["raw"]).max()
+    assert err <= 3e-5 * max(1.0, np.abs(g["raw"]).max()), err
+    out = oracle.render(raw.reshape(64, 64, 4), g["t_values"], True)
+    np.testing.assert_allclose(out.color, g["color"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(out.alpha, g["alpha"], rtol=0, atol=2e-5)
+
+
+def test_positional_b_values_matches_reference_buffer():
+    g = load("ffmlp_positional.npz")
+    # non-integer exponents: powf differs by <=1 ulp between libm and ATen; the
+    # product always reads b_values from the model's own buffer, never recomputes it
+    np.testing.assert_allclose(oracle.positional_b_values(5.5, 256, 3), g["w.b_values"], rtol=1.2e-7)
+    n = load("nerf_render.npz")
+    assert np.array_equal(oracle.nerf_encoding_matrix(9, 10), n["w.pos_encoding"])
+    assert np.array_equal(oracle.nerf_encoding_matrix(3, 4), n["w.view_encoding"])
+
+
+def test_focus_sampling():
+    g = load("focus.npz")
+    near, far = g["near_far"]
+    s = oracle.sample_rays(g["starts"], g["directions"], near, far, 32, u=g["u_uniform"],
+                           cdf=g["cdfs"], u_focus=g["u_focus"], focus_stratified=True)
+    np.testing.assert_allclose(s.t_values, g["t_values"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(s.positions, g["positions"], rtol=0, atol=2e-6)
+    s = oracle.sample_rays(g["starts"], g["directions"], near, far, 32, u=None,
+                           cdf=g["cdfs"], focus_stratified=False)
+    np.testing.assert_allclose(s.t_values, g["t_det"], rtol=0, atol=1e-6)
+
+
+def test_determine_cdf_via_reference_cdfs():
+    """CDF rows from the reference are monotone, start at 0, end at 1; the oracle
+    reproduces them from the oracle's own coarse sigma pass."""
+    g = load("focus.npz")
+    n = load("nerf_render.npz")
+    p = weights(n)
+    near, far = g["near_far"]
+    t = oracle.linspace(near, far, 16)
+    pos = g["starts"][:, None, :] + t[..., None] * g["directions"][:, None, :]
+    dirs = np.repeat(g["directions"][:, None, :], 16, 1)
+    raw = oracle.nerf_forward(p, pos.reshape(-1, 3).astype(np.float32), dirs.reshape(-1, 3))
+    sigma = oracle.softplus(raw[:, 3]).reshape(-1, 16)
+    cdf = oracle.determine_cdf(t, sigma)
+    np.testing.assert_allclose(cdf, g["cdfs"], rtol=0, atol=5e-5)
