@@ -1,0 +1,25 @@
+"""B200-native volume-rendering hot path with the API of ``fourier_feature_nets``.
+
+Public names mirror the reference package (fourier_feature_nets/__init__.py:3-35) for the
+render/training path: ``Raycaster``, ``RaySampler``, ``RaySamples``, ``NeRF``,
+``FourierFeatureMLP`` (+ presets), ``CameraInfo``, ``Resolution``, ``RenderResult``,
+``calculate_blend_weights``, ``exponential_lr_decay``, ``load_model``, ``orbit``.
+"""
+from .camera_info import CameraInfo, Resolution
+from .fourier_feature_models import (BasicFourierMLP, FourierFeatureMLP, GaussianFourierMLP, MLP,
+                                     PositionalFourierMLP)
+from .nerf_model import NeRF
+from .ray_caster import Raycaster
+from .ray_dataset_modes import Mode
+from .ray_sampler import RayBundle, RaySampler, RaySamples
+from .utils import (RenderResult, calculate_blend_weights, exponential_lr_decay, linspace,
+                    load_model, orbit)
+
+RayCaster = Raycaster   # BASELINE.json spells it this way; the reference class is ``Raycaster``
+
+__version__ = "0.1.0"
+
+__all__ = ["CameraInfo", "Resolution", "MLP", "NeRF", "BasicFourierMLP", "FourierFeatureMLP",
+           "PositionalFourierMLP", "GaussianFourierMLP", "Raycaster", "RayCaster", "RaySampler",
+           "RaySamples", "RayBundle", "RenderResult", "Mode", "calculate_blend_weights",
+           "exponential_lr_decay", "linspace", "load_model", "orbit", "__version__"]

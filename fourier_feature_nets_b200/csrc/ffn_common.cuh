@@ -1,0 +1,110 @@
+// Shared definitions for libffn_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace ffn {
+
+// ----------------------------------------------------------------------------------------
+// Tile / shared-memory geometry of the fused render kernel
+// ----------------------------------------------------------------------------------------
+constexpr int kTileM = 128;                    // rows (samples) per tile == UMMA M == TMEM lanes
+constexpr int kChunkK = 64;                    // K elements per 128-byte swizzled row
+constexpr int kChunkBytesA = kTileM * 128;     // one K-chunk of an A tile: 16 KiB
+constexpr int kActChunks = 4;                  // 256-wide hidden activation
+constexpr int kEncChunk = 4;                   // chunk index of the encoding tile inside a slot
+constexpr int kSlotChunks = 5;
+constexpr int kSlotBytes = kSlotChunks * kChunkBytesA;   // 80 KiB
+constexpr int kWStageBytes = 256 * 128;        // one weight K-chunk (N=256 x K=64): 32 KiB
+constexpr int kWStages = 2;
+constexpr int kSmemW = 0;
+constexpr int kSmemSlot0 = kWStages * kWStageBytes;             // 64 KiB
+constexpr int kSmemMisc = kSmemSlot0 + 2 * kSlotBytes;          // 224 KiB
+constexpr int kSmemMiscBytes = 3072;
+constexpr int kSmemTotal = kSmemMisc + kSmemMiscBytes;          // 232448 = 227 KiB (the sm_100 maximum)
+
+constexpr int kMaxMmaLayers = 12;
+constexpr int kMaxChunksPerLayer = 6;
+constexpr int kThreads = 384;                  // warp 0 producer, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 / 8-11 epilogue
+
+// epilogue kinds
+enum : uint8_t {
+  EPI_RELU_ACT = 0,     // act = relu(acc + b)        -> next A operand
+  EPI_LINEAR_ACT = 1,   // act = acc + b              -> next A operand
+  EPI_RELU_HEAD = 2,    // h = relu(acc + b); out[0 .. head_n) = head_w . h + head_b ; no A write
+  EPI_ENC_PART2 = 3,    // no accumulator read: write the second half of a wide encoding into act chunks
+};
+
+struct LayerDesc {
+  uint32_t w_offset;                       // byte offset of this layer's packed weights
+  uint16_t n;                              // UMMA N (256 or 128)
+  uint8_t n_chunks;
+  uint8_t epi;                             // EPI_*
+  uint8_t accumulate;                      // 1: first MMA accumulates onto the existing TMEM tile
+  uint8_t sigma_head;                      // 1: also emit out[3] = head_w[3] . h + head_b[3] from this layer's fp32 h
+  uint8_t write_view_enc;                  // 1: after this layer, overwrite the enc chunk with the view encoding
+  uint8_t bias_row;                        // row of ConstParams::bias
+  uint8_t src[kMaxChunksPerLayer];         // A chunk index (0..3 act, 4 enc) per K-chunk
+  uint8_t ksteps[kMaxChunksPerLayer];      // UMMA K-steps (of 16) per K-chunk
+  uint8_t head_n, pad0, pad1, pad2;     // EPI_RELU_HEAD: outputs 0..head_n-1
+};
+
+// encodings
+enum : int32_t { ENC_NERF = 0, ENC_FFMLP = 1, ENC_NONE = 2 };
+
+// input modes
+enum : int32_t { MODE_POINTS = 0, MODE_SAMPLES = 1, MODE_RAYS = 2 };
+
+// Broadcast-read parameters: biases, head weights, frequency tables.  Lives in
+// __constant__ memory; re-uploaded (device-to-device, stream ordered) whenever the
+// active net or its weights change.
+struct ConstParams {
+  float bias[kMaxMmaLayers][256];
+  float head_w[4][256];
+  float head_b[4];
+  float freq_pos[16];
+  float freq_view[16];
+};
+
+struct KernelArgs {
+  const uint8_t* wpack;
+  LayerDesc layers[kMaxMmaLayers];
+  int32_t num_layers;
+  int32_t enc_kind;
+  int32_t f_pos, f_view, include_inputs, use_view;
+  int32_t emb;                 // FFMLP embedding size E
+  const float* ffm_b;          // FFMLP: device (3,E) b_values
+  const float* ffm_a;          // FFMLP: device (E) a_values
+  int32_t bf16;
+  // inputs
+  int32_t mode;
+  const float* pos;            // POINTS (M,3) / SAMPLES (R,S,3)
+  const float* dir;            // POINTS (M,3) / SAMPLES (R,S,3) / RAYS (R,3)
+  const float* tvals;          // SAMPLES (R,S)
+  const float* org;            // RAYS (R,3)
+  const float* near_;          // RAYS (R)
+  const float* far_;           // RAYS (R)
+  const float* lin;            // RAYS (S)
+  const float* jitter;         // RAYS (R,S) or null
+  unsigned long long seed;
+  long long ray_offset;
+  int32_t stratified;
+  long long M;                 // total rows
+  int32_t S;                   // samples per ray (fused / rays modes)
+  int32_t fused;               // 1: composite in-kernel (S power of two <= 128)
+  // outputs
+  float* raw;                  // (M,4) when !fused
+  float* t_out;                // (M) optional (RAYS)
+  float* rgb;                  // (R,3)
+  float* alpha;                // (R)
+  float* depth;                // (R) or null
+  int32_t* nan_flag;
+  // debug
+  int32_t dbg_layer;
+  float* dbg_out;              // (M,256)
+  int32_t num_tiles;
+};
+
+}  // namespace ffn

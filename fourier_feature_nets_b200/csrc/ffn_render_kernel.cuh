@@ -1,0 +1,509 @@
+// The fused render kernel: sampling -> Fourier encoding -> MLP on tcgen05 -> compositing.
+//
+// One persistent CTA per SM, 384 threads:
+//   warp 0      weight producer: streams the packed (pre-swizzled) weight K-chunks of every
+//               layer through a 2-stage shared-memory ring with the bulk-copy (TMA) engine
+//   warp 1      UMMA issuer: one lane issues tcgen05.mma (M=128, N=256|128, K=16) for the
+//               tile in slot 0 then slot 1 of each layer, committing to mbarriers
+//   warp 2      allocates / frees the 512 TMEM columns (two 128x256 fp32 accumulators)
+//   warps 4-7   epilogue warpgroup of slot 0     } thread == row == sample: inputs, encoding,
+//   warps 8-11  epilogue warpgroup of slot 1     } TMEM -> bias/ReLU -> fp16 A tile, heads,
+//                                                  transmittance scan, pixel outputs
+// The two slots are staggered by one layer, so the tensor core works on slot B while slot A's
+// epilogue converts its accumulator into the next layer's A operand, and vice versa.
+#pragma once
+#include "ffn_common.cuh"
+#include "ffn_ptx.cuh"
+
+namespace ffn {
+
+__constant__ ConstParams c_params;
+
+// ----------------------------------------------------------------------------------------
+// math helpers
+// ----------------------------------------------------------------------------------------
+
+// sin/cos of an arbitrary fp32 argument: 3-term Cody-Waite reduction by 2*pi (exact for
+// |x| < ~2^15 * 6.28) followed by the MUFU approximations on [-pi, pi] (abs err ~4e-7).
+__device__ __forceinline__ void sincos_rr(float x, float& s, float& c) {
+  const float kInv2Pi = 0.15915494309189535f;
+  const float kMagic = 12582912.0f;  // 1.5 * 2^23: (x + magic) - magic == rint(x)
+  float n = __fadd_rn(__fmaf_rn(x, kInv2Pi, kMagic), -kMagic);
+  float r = __fmaf_rn(n, -6.28125f, x);
+  r = __fmaf_rn(n, -1.9353071693331003e-3f, r);
+  r = __fmaf_rn(n, -1.0253350219e-11f, r);
+  s = __sinf(r);
+  c = __cosf(r);
+}
+
+__device__ __forceinline__ float softplus_f(float x) {
+  // F.softplus(beta=1, threshold=20): ray_caster.py:71
+  return x > 20.f ? x : log1pf(expf(x));
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+// Philox4x32-10 -> one uniform in [0,1) with 24 random bits for (ray, sample)
+__device__ __forceinline__ float philox_uniform(unsigned long long seed, unsigned long long ray,
+                                                uint32_t sample) {
+  uint32_t c0 = static_cast<uint32_t>(ray), c1 = static_cast<uint32_t>(ray >> 32), c2 = sample >> 2,
+           c3 = 0x5eed5eedu;
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  uint32_t sel = sample & 3u;
+  uint32_t r = sel == 0 ? c0 : sel == 1 ? c1 : sel == 2 ? c2 : c3;
+  return static_cast<float>(r >> 8) * (1.0f / 16777216.0f);
+}
+
+// ----------------------------------------------------------------------------------------
+// encoding tiles.  Column order inside the 64-wide encoding chunk is OURS (the weight
+// columns are permuted to match at pack time):  col 6k+2j = cos(f_k x_j), col 6k+2j+1 =
+// sin(f_k x_j)  (k < 10, j < 3), cols 60..62 = x, col 63 = 0.
+// ----------------------------------------------------------------------------------------
+template <bool kBF16>
+__device__ __forceinline__ void write_enc_posenc(uint32_t row_addr, uint32_t row7, float x0,
+                                                 float x1, float x2, const float* freq, int nfreq,
+                                                 bool include_inputs) {
+  uint32_t pk[32];
+  const float x[3] = {x0, x1, x2};
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    if (k < nfreq) {
+      const float f = freq[k];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        float s, c;
+        sincos_rr(__fmul_rn(x[j], f), s, c);
+        pk[3 * k + j] = ptx::pack2<kBF16, false>(c, s);
+      }
+    } else {
+      pk[3 * k] = pk[3 * k + 1] = pk[3 * k + 2] = 0u;
+    }
+  }
+  pk[30] = include_inputs ? ptx::pack2<kBF16, false>(x0, x1) : 0u;
+  pk[31] = include_inputs ? ptx::pack2<kBF16, false>(x2, 0.f) : 0u;
+#pragma unroll
+  for (uint32_t u = 0; u < 8; ++u)
+    ptx::st_shared_v4(row_addr + ((u ^ row7) << 4), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2],
+                      pk[4 * u + 3]);
+}
+
+// FourierFeatureMLP encoding (fourier_feature_models.py:66-68): feature e of (pi x) @ B gives
+// the column pair (2e, 2e+1) = (a_e cos, a_e sin).  Writes features [e0, e0 + 32*nchunks) into
+// consecutive chunks starting at chunk_addr (row-relative), zero padding beyond E.
+template <bool kBF16>
+__device__ __forceinline__ void write_enc_ffmlp(uint32_t row_addr0, uint32_t row7, float x0, float x1,
+                                                float x2, const float* __restrict__ bmat,
+                                                const float* __restrict__ avec, int E, int e0,
+                                                int nchunks) {
+  const float kPi = 3.14159265358979323846f;
+  const float p0 = __fmul_rn(kPi, x0), p1 = __fmul_rn(kPi, x1), p2 = __fmul_rn(kPi, x2);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const uint32_t row_addr = row_addr0 + ch * kChunkBytesA;
+#pragma unroll
+    for (uint32_t u = 0; u < 8; ++u) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = e0 + ch * 32 + u * 4 + q;
+        if (e < E) {
+          // (pi x) @ B in index order, fp32 (one rounding per multiply-add like ATen's addmm)
+          float arg = __fmul_rn(p0, __ldg(bmat + e));
+          arg = __fmaf_rn(p1, __ldg(bmat + E + e), arg);
+          arg = __fmaf_rn(p2, __ldg(bmat + 2 * E + e), arg);
+          float s, c;
+          sincos_rr(arg, s, c);
+          const float a = __ldg(avec + e);
+          pk[q] = ptx::pack2<kBF16, false>(__fmul_rn(a, c), __fmul_rn(a, s));
+        } else {
+          pk[q] = 0u;
+        }
+      }
+      ptx::st_shared_v4(row_addr + ((u ^ row7) << 4), pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+// raw inputs as the (only) features: cols 0..2 = x, rest zero (the un-encoded MLP preset)
+template <bool kBF16>
+__device__ __forceinline__ void write_enc_raw(uint32_t row_addr, uint32_t row7, float x0, float x1,
+                                              float x2) {
+#pragma unroll
+  for (uint32_t u = 0; u < 8; ++u) {
+    uint32_t a = 0, b = 0;
+    if (u == 0) {
+      a = ptx::pack2<kBF16, false>(x0, x1);
+      b = ptx::pack2<kBF16, false>(x2, 0.f);
+    }
+    ptx::st_shared_v4(row_addr + ((u ^ row7) << 4), a, b, 0u, 0u);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// the kernel
+// ----------------------------------------------------------------------------------------
+template <bool kBF16>
+__global__ void __launch_bounds__(kThreads, 1)
+ffn_render_kernel(const __grid_constant__ KernelArgs args) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // misc region
+  const uint32_t bars = smem_base + kSmemMisc;
+  const uint32_t bar_w_full = bars + 0;     // [2]
+  const uint32_t bar_w_empty = bars + 16;   // [2]
+  const uint32_t bar_a_ready = bars + 32;   // [2]
+  const uint32_t bar_acc_full = bars + 48;  // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kSmemMisc + 128);
+  float* scratch_base = reinterpret_cast<float*>(smem + kSmemMisc + 256);
+
+  if ((smem_base & 1023u) != 0u) {  // SWIZZLE_128B operands need 1024-byte aligned chunks
+    if (threadIdx.x == 0 && args.nan_flag) atomicOr(args.nan_flag, 0x40000000);
+    return;
+  }
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(bar_w_full + 8 * i, 1);
+      ptx::mbar_init(bar_w_empty + 8 * i, 1);
+      ptx::mbar_init(bar_a_ready + 8 * i, 4);   // one arrive per epilogue warp
+      ptx::mbar_init(bar_acc_full + 8 * i, 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // static round-robin tile schedule: local tile k of this CTA is global tile blockIdx.x + k*grid,
+  // processed in slot k & 1
+  const int num_tiles = args.num_tiles;
+  const int my_tiles =
+      (int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int L = args.num_layers;
+
+  if (warp == 0) {
+    // ================================================================ weight producer
+    uint32_t stage = 0, phase = 0;
+    for (int kp = 0; kp < my_tiles; kp += 2) {
+      const int nslots = min(2, my_tiles - kp);
+      for (int l = 0; l < L; ++l) {
+        const LayerDesc& ld = args.layers[l];
+        const uint32_t bytes = (uint32_t)ld.n * 128u;
+        for (int s = 0; s < nslots; ++s) {
+          for (int c = 0; c < ld.n_chunks; ++c) {
+            ptx::mbar_wait(bar_w_empty + 8 * stage, phase ^ 1u);
+            if (lane == 0) {
+              ptx::mbar_arrive_expect_tx(bar_w_full + 8 * stage, bytes);
+              ptx::bulk_g2s(smem_base + kSmemW + stage * kWStageBytes,
+                            args.wpack + ld.w_offset + (size_t)c * bytes, bytes,
+                            bar_w_full + 8 * stage);
+            }
+            __syncwarp();
+            if (++stage == kWStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ UMMA issuer
+    uint32_t stage = 0, phase = 0;
+    uint32_t a_phase[2] = {0u, 0u};
+    for (int kp = 0; kp < my_tiles; kp += 2) {
+      const int nslots = min(2, my_tiles - kp);
+      for (int l = 0; l < L; ++l) {
+        const LayerDesc& ld = args.layers[l];
+        const uint32_t idesc = ptx::make_idesc_f16(ld.n, kBF16);
+        for (int s = 0; s < nslots; ++s) {
+          ptx::mbar_wait(bar_a_ready + 8 * s, a_phase[s]);
+          a_phase[s] ^= 1u;
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)s * 256u;
+          const uint32_t slot_base = smem_base + kSmemSlot0 + s * kSlotBytes;
+          uint32_t accumulate = ld.accumulate;
+          for (int c = 0; c < ld.n_chunks; ++c) {
+            ptx::mbar_wait(bar_w_full + 8 * stage, phase);
+            ptx::tc_fence_after();
+            if (lane == 0) {
+              const uint32_t a_addr = slot_base + (uint32_t)ld.src[c] * kChunkBytesA;
+              const uint32_t b_addr = smem_base + kSmemW + stage * kWStageBytes;
+              const int ks_n = ld.ksteps[c];
+              for (int ks = 0; ks < ks_n; ++ks) {
+                ptx::umma_f16(d_tmem, ptx::make_kmajor_sw128_desc(a_addr + ks * 32),
+                              ptx::make_kmajor_sw128_desc(b_addr + ks * 32), idesc, accumulate);
+                accumulate = 1u;
+              }
+              ptx::umma_commit(bar_w_empty + 8 * stage);   // frees the weight stage when the MMAs retire
+              if (c == ld.n_chunks - 1) ptx::umma_commit(bar_acc_full + 8 * s);
+            }
+            __syncwarp();
+            if (++stage == kWStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================ epilogue warpgroups
+    const int slot = (warp - 4) >> 2;
+    const int wq = warp & 3;                       // TMEM lane quadrant of this warp
+    const int row = wq * 32 + lane;                // row inside the tile == TMEM lane
+    const uint32_t row7 = (uint32_t)row & 7u;
+    const uint32_t slot_base = smem_base + kSmemSlot0 + slot * kSlotBytes;
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t enc_row_addr = slot_base + kEncChunk * kChunkBytesA + row_off;
+    const uint32_t taddr_base = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)slot * 256u;
+    const uint32_t my_a_ready = bar_a_ready + 8 * slot;
+    const uint32_t my_acc_full = bar_acc_full + 8 * slot;
+    float* sc_t = scratch_base + slot * 320;       // [128] t values of the tile
+    float* sc_part = sc_t + 128;                   // [4][8] per-warp partials
+    uint32_t acc_phase = 0;
+    const int S = args.S;
+
+    for (int k = slot; k < my_tiles; k += 2) {
+      const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
+      const long long row_g = tile * kTileM + row;
+      const bool valid = row_g < args.M;
+
+      // ------------------------------------------------ inputs for this row (sample)
+      float px = 0.f, py = 0.f, pz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, tval = 0.f;
+      long long ray = 0;
+      int sidx = 0;
+      if (valid) {
+        if (args.mode == MODE_RAYS) {
+          ray = row_g / S;
+          sidx = (int)(row_g - ray * S);
+          const float nr = __ldg(args.near_ + ray), fr = __ldg(args.far_ + ray);
+          const float diff = __fsub_rn(fr, nr);
+          // utils.py:190-194 then ray_sampler.py:381-386, same rounding sequence
+          tval = __fadd_rn(nr, __fmul_rn(__ldg(args.lin + sidx), diff));
+          if (args.stratified) {
+            const float scale = __fdiv_rn(diff, (float)S);
+            const float u = args.jitter ? __ldg(args.jitter + row_g)
+                                        : philox_uniform(args.seed, (unsigned long long)(args.ray_offset + ray),
+                                                         (uint32_t)sidx);
+            tval = __fadd_rn(tval, __fmul_rn(u, scale));
+          }
+          dx = __ldg(args.dir + ray * 3 + 0);
+          dy = __ldg(args.dir + ray * 3 + 1);
+          dz = __ldg(args.dir + ray * 3 + 2);
+          // ray_sampler.py:397: positions = starts + t * directions
+          px = __fadd_rn(__ldg(args.org + ray * 3 + 0), __fmul_rn(tval, dx));
+          py = __fadd_rn(__ldg(args.org + ray * 3 + 1), __fmul_rn(tval, dy));
+          pz = __fadd_rn(__ldg(args.org + ray * 3 + 2), __fmul_rn(tval, dz));
+          if (args.t_out) args.t_out[row_g] = tval;
+        } else {
+          px = __ldg(args.pos + row_g * 3 + 0);
+          py = __ldg(args.pos + row_g * 3 + 1);
+          pz = __ldg(args.pos + row_g * 3 + 2);
+          if (args.use_view) {
+            dx = __ldg(args.dir + row_g * 3 + 0);
+            dy = __ldg(args.dir + row_g * 3 + 1);
+            dz = __ldg(args.dir + row_g * 3 + 2);
+          }
+          if (args.mode == MODE_SAMPLES) {
+            ray = row_g / S;
+            sidx = (int)(row_g - ray * S);
+            tval = __ldg(args.tvals + row_g);
+          }
+        }
+      }
+
+      // ------------------------------------------------ first-layer A operand
+      if (args.enc_kind == ENC_NERF) {
+        write_enc_posenc<kBF16>(enc_row_addr, row7, px, py, pz, c_params.freq_pos, args.f_pos,
+                                args.include_inputs != 0);
+      } else if (args.enc_kind == ENC_FFMLP) {
+        // features [0,128) -> act chunks 0..3, [128,160) -> enc chunk
+        write_enc_ffmlp<kBF16>(slot_base + row_off, row7, px, py, pz, args.ffm_b, args.ffm_a,
+                               args.emb, 0, 5);
+      } else {
+        write_enc_raw<kBF16>(enc_row_addr, row7, px, py, pz);
+      }
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(my_a_ready);
+
+      float out[4] = {0.f, 0.f, 0.f, 0.f};  // raw rgb | sigma of this sample
+
+      for (int l = 0; l < L; ++l) {
+        const LayerDesc& ld = args.layers[l];
+        ptx::mbar_wait(my_acc_full, acc_phase);
+        acc_phase ^= 1u;
+        ptx::tc_fence_after();
+
+        if (ld.epi == EPI_ENC_PART2) {
+          // wide FourierFeatureMLP encodings: features [160, 256) -> act chunks 0..2
+          write_enc_ffmlp<kBF16>(slot_base + row_off, row7, px, py, pz, args.ffm_b, args.ffm_a,
+                                 args.emb, 160, 3);
+        } else {
+          const float* __restrict__ bias = c_params.bias[ld.bias_row];
+          const int nblk = ld.n >> 5;
+          const bool relu = ld.epi != EPI_LINEAR_ACT;
+          const bool to_act = ld.epi != EPI_RELU_HEAD;
+          float hacc[4] = {0.f, 0.f, 0.f, 0.f};
+          const int hn = ld.epi == EPI_RELU_HEAD ? ld.head_n : 0;   // heads 0..hn-1 (rgb | rgb+sigma)
+          for (int b = 0; b < nblk; ++b) {
+            uint32_t v[32];
+            ptx::tmem_ld32(taddr_base + (uint32_t)b * 32u, v);
+            ptx::tmem_wait_ld(v);
+            const int c0 = b * 32;
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float t = __uint_as_float(v[j]) + bias[c0 + j];
+              x[j] = relu ? fmaxf(t, 0.f) : t;
+            }
+            if (ld.sigma_head) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) hacc[3] = fmaf(x[j], c_params.head_w[3][c0 + j], hacc[3]);
+            }
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              if (o < hn) {
+                float a = hacc[o];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a = fmaf(x[j], c_params.head_w[o][c0 + j], a);
+                hacc[o] = a;
+              }
+            }
+            if (args.dbg_layer == l && valid) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) args.dbg_out[row_g * 256 + c0 + j] = x[j];
+            }
+            if (to_act) {
+              const uint32_t chunk_addr = slot_base + (uint32_t)(c0 >> 6) * kChunkBytesA + row_off;
+              const uint32_t u0 = (uint32_t)(c0 & 63) >> 3;
+#pragma unroll
+              for (uint32_t q = 0; q < 4; ++q) {
+                ptx::st_shared_v4(chunk_addr + (((u0 + q) ^ row7) << 4),
+                                  ptx::pack2<kBF16, false>(x[8 * q + 0], x[8 * q + 1]),
+                                  ptx::pack2<kBF16, false>(x[8 * q + 2], x[8 * q + 3]),
+                                  ptx::pack2<kBF16, false>(x[8 * q + 4], x[8 * q + 5]),
+                                  ptx::pack2<kBF16, false>(x[8 * q + 6], x[8 * q + 7]));
+              }
+            }
+          }
+          if (ld.sigma_head) out[3] = hacc[3] + c_params.head_b[3];
+#pragma unroll
+          for (int o = 0; o < 4; ++o)
+            if (o < hn) out[o] = hacc[o] + c_params.head_b[o];
+        }
+
+        if (ld.write_view_enc) {
+          write_enc_posenc<kBF16>(enc_row_addr, row7, dx, dy, dz, c_params.freq_view, args.f_view,
+                                  args.include_inputs != 0);
+        }
+        if (l < L - 1) {
+          ptx::fence_proxy_async();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(my_a_ready);
+        }
+      }
+      ptx::tc_fence_before();
+
+      // ------------------------------------------------ outputs
+      if (!args.fused) {
+        if (valid && args.raw)
+          reinterpret_cast<float4*>(args.raw)[row_g] = make_float4(out[0], out[1], out[2], out[3]);
+        continue;
+      }
+
+      // ray_caster.py:67-93 + utils.py:72-97, one thread per sample, S | 128
+      const float cr = sigmoid_f(out[0]), cg = sigmoid_f(out[1]), cb = sigmoid_f(out[2]);
+      const float sigma = softplus_f(out[3]);
+      if (valid && (isnan(cr) || isnan(cg) || isnan(cb) || isnan(sigma))) atomicOr(args.nan_flag, 1);
+      const uint32_t bar_id = 1 + slot;
+      sc_t[row] = tval;
+      ptx::named_bar_sync(bar_id, 128);
+      const bool last = sidx == S - 1;
+      const float delta = last ? 1e10f : __fsub_rn(sc_t[min(row + 1, 127)], tval);
+      const float al = __fsub_rn(1.f, expf(-__fmul_rn(sigma, delta)));
+      const float tr = fminf(1.f, __fadd_rn(__fsub_rn(1.f, al), 1e-10f));
+      // exclusive product scan over the samples of the ray
+      const int seg = S < 32 ? S : 32;
+      const int sl = lane & (seg - 1);
+      float inc = tr;
+      for (int off = 1; off < seg; off <<= 1) {
+        const float o = __shfl_up_sync(0xffffffffu, inc, off);
+        if (sl >= off) inc *= o;
+      }
+      float T = __shfl_up_sync(0xffffffffu, inc, 1);
+      if (sl == 0) T = 1.f;
+      const int wpr = S >> 5;  // warps per ray (0 when S < 32)
+      if (wpr > 1) {
+        if (lane == 31) sc_part[wq * 8 + 7] = inc;
+        ptx::named_bar_sync(bar_id, 128);
+        const int w0 = wq & ~(wpr - 1);
+        for (int w = w0; w < wq; ++w) T *= sc_part[w * 8 + 7];
+      }
+      const float wgt = al * T;
+      // reductions over the ray: sum(w c) over all samples, sum(w) and first argmax(w) over s < S-1
+      float r0 = wgt * cr, r1 = wgt * cg, r2 = wgt * cb, r3 = last ? 0.f : wgt;
+      float bw = last ? -1.f : wgt;
+      int bs = sidx;
+      for (int off = seg >> 1; off > 0; off >>= 1) {
+        r0 += __shfl_xor_sync(0xffffffffu, r0, off);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, off);
+        r2 += __shfl_xor_sync(0xffffffffu, r2, off);
+        r3 += __shfl_xor_sync(0xffffffffu, r3, off);
+        const float ow = __shfl_xor_sync(0xffffffffu, bw, off);
+        const int os = __shfl_xor_sync(0xffffffffu, bs, off);
+        if (ow > bw || (ow == bw && os < bs)) { bw = ow; bs = os; }
+      }
+      if (wpr > 1) {
+        if (lane == 0) {
+          sc_part[wq * 8 + 0] = r0; sc_part[wq * 8 + 1] = r1; sc_part[wq * 8 + 2] = r2;
+          sc_part[wq * 8 + 3] = r3; sc_part[wq * 8 + 4] = bw; sc_part[wq * 8 + 5] = __int_as_float(bs);
+        }
+        ptx::named_bar_sync(bar_id, 128);
+        if (sidx == 0) {
+          r0 = r1 = r2 = r3 = 0.f; bw = -2.f; bs = 0;
+          for (int w = wq; w < wq + wpr; ++w) {
+            r0 += sc_part[w * 8 + 0]; r1 += sc_part[w * 8 + 1]; r2 += sc_part[w * 8 + 2];
+            r3 += sc_part[w * 8 + 3];
+            const float ow = sc_part[w * 8 + 4];
+            const int os = __float_as_int(sc_part[w * 8 + 5]);
+            if (ow > bw || (ow == bw && os < bs)) { bw = ow; bs = os; }
+          }
+        }
+      }
+      if (valid && sidx == 0) {
+        args.rgb[ray * 3 + 0] = r0;
+        args.rgb[ray * 3 + 1] = r1;
+        args.rgb[ray * 3 + 2] = r2;
+        args.alpha[ray] = r3;
+        if (args.depth) {
+          const int cut = (r3 < 0.1f || S == 1) ? S - 1 : bs;   // ray_caster.py:86-89
+          args.depth[ray] = sc_t[row + cut];
+        }
+      }
+      // sc_t / sc_part are rewritten by the next tile only after its first named barrier
+      ptx::named_bar_sync(bar_id, 128);
+    }
+  }
+
+  // ---------------------------------------------------------------- teardown
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace ffn

@@ -1,0 +1,70 @@
+"""Binds an ``nn.Module`` (NeRF / FourierFeatureMLP) to its packed tensor-core image.
+
+The packed image is rebuilt on the GPU (``ffn_net_pack``) whenever a parameter
+changed -- detected through the tensors' in-place version counters, so an
+optimiser step costs two small kernel launches and no host synchronisation.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_OPERAND = {"fp16": _lib.OPERAND_FP16, "bf16": _lib.OPERAND_BF16}
+DEFAULT_OPERAND = "fp16"
+
+
+def _linear_list(model) -> List[torch.nn.Linear]:
+    kind = getattr(model, "_ffn_kind", None)
+    if kind == "nerf":
+        return list(model.layers) + [model.opacity_out, model.bottleneck, model.hidden_view,
+                                     model.color_out]
+    if kind == "fourier":
+        return list(model.layers)
+    raise _lib.FFNError("model type %s has no libffn_b200 engine" % type(model).__name__)
+
+
+def supported(model) -> bool:
+    return getattr(model, "_ffn_kind", None) in ("nerf", "fourier")
+
+
+class Engine:
+    def __init__(self, model, device: torch.device, operand: str):
+        self.device = device
+        self.operand = operand
+        kind = model._ffn_kind
+        if kind == "nerf":
+            p = model.params
+            # pos_encoding[j, 3k+j] = f_k  (nerf_model.py:77-84)
+            freq_pos = [float(model.pos_encoding[0, 3 * k]) for k in range(p["num_freq_pos"])]
+            freq_view = [float(model.view_encoding[0, 3 * k]) for k in range(p["num_freq_view"])]
+            self.net = _lib.Net.nerf(p["num_layers"], p["num_channels"], freq_pos, freq_view,
+                                     p["skips"], p["include_inputs"], device, _OPERAND[operand])
+        else:
+            hidden = len(model.layers) - 1
+            chans = {l.out_features for l in list(model.layers)[:-1]}
+            if chans != {256} or model.layers[-1].out_features != 4 or model.num_inputs != 3:
+                raise _lib.FFNError("libffn_b200 supports 3 -> [256]*n -> 4 FourierFeatureMLPs")
+            self.net = _lib.Net.ffmlp(hidden, 256, model.a_values, model.b_values, device,
+                                      _OPERAND[operand])
+        self._sig: Optional[Tuple] = None
+
+    def sync_weights(self, model):
+        lins = _linear_list(model)
+        sig = tuple((l.weight.data_ptr(), l.weight._version, l.bias.data_ptr(), l.bias._version)
+                    for l in lins)
+        if sig != self._sig:
+            self.net.pack([l.weight for l in lins], [l.bias for l in lins])
+            self._sig = sig
+
+
+def get_engine(model, device: torch.device, operand: Optional[str] = None) -> Engine:
+    operand = operand or getattr(model, "ffn_operand", DEFAULT_OPERAND)
+    eng = model.__dict__.get("_ffn_engine")
+    if eng is None or eng.device != device or eng.operand != operand:
+        eng = Engine(model, device, operand)
+        model.__dict__["_ffn_engine"] = eng
+    eng.sync_weights(model)
+    return eng

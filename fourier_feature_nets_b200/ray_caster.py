@@ -1,0 +1,221 @@
+"""``Raycaster`` with the reference's API (fourier_feature_nets/ray_caster.py:36-376).
+
+``render`` on CUDA without autograd is ONE launch of the fused sm_100a kernel
+(sampling -> encoding -> MLP on tcgen05 -> compositing); under autograd it is the
+plain differentiable definition of the same maths (training kernels: DESIGN.md).
+"""
+import copy
+import time
+from typing import List, NamedTuple, Optional, OrderedDict
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from . import engine as _engine
+from .nerf_model import _needs_grad
+from .ray_sampler import RayBundle, RaySampler, RaySamples
+from .utils import RenderResult, blend_weights_torch, exponential_lr_decay
+
+LogEntry = NamedTuple("LogEntry", [("step", int), ("timestamp", float),
+                                   ("state", OrderedDict[str, torch.Tensor]),
+                                   ("train_psnr", float), ("val_psnr", float)])
+
+
+class Raycaster(nn.Module):
+    """Differentiable volumetric raycaster around a radiance-field model."""
+
+    def __init__(self, model: nn.Module):
+        super().__init__()
+        self.model = model
+        self.check_nan_every_call = False   # True: reference behaviour (a host sync per render)
+        self._lin_cache = {}
+
+    # ---- the hot path -----------------------------------------------------------------
+    def _lin(self, num_samples: int, device) -> torch.Tensor:
+        key = (num_samples, str(device))
+        if key not in self._lin_cache:
+            self._lin_cache[key] = torch.linspace(0, 1, num_samples).to(device)
+        return self._lin_cache[key]
+
+    def render(self, ray_samples: RaySamples, include_depth=False) -> RenderResult:
+        """Render the ray samples -> per-ray colour (R,3), alpha (R), depth (R)."""
+        device = next(self.model.parameters()).device
+        fused = device.type == "cuda" and _engine.supported(self.model) and not _needs_grad(self.model)
+        if not fused:
+            if device.type == "cuda" and not _engine.supported(self.model):
+                raise _lib.FFNError("no libffn_b200 engine for %s" % type(self.model).__name__)
+            return self._render_torch(ray_samples, include_depth)
+
+        eng = _engine.get_engine(self.model, device)
+        if isinstance(ray_samples, RayBundle):
+            b = ray_samples
+            color, alpha, depth, _ = eng.net.render_rays(
+                b.starts, b.directions, b.near, b.far, self._lin(b.num_samples, device), b.jitter,
+                b.stratified, b.seed, 0, b.num_samples, include_depth)
+        else:
+            views = ray_samples.view_directions if self.model.use_view else None
+            color, alpha, depth = eng.net.render_samples(ray_samples.positions, views,
+                                                         ray_samples.t_values, include_depth)
+        if self.check_nan_every_call:
+            self.check_nan()
+        return RenderResult(color, alpha, depth)
+
+    def check_nan(self):
+        """Raise like the reference's asserts (ray_caster.py:73-74) if any render since the
+        last check produced a NaN colour or opacity.  One device->host read."""
+        eng = self.model.__dict__.get("_ffn_engine")
+        if eng is not None:
+            flag = eng.net.nan_flag()
+            assert not (flag & 0x40000000), "libffn_b200: shared memory base is not 1024-byte aligned"
+            assert not (flag & 1), "NaN in rendered colour/opacity"
+
+    def _render_torch(self, ray_samples: RaySamples, include_depth: bool) -> RenderResult:
+        """Differentiable definition (ray_caster.py:60-93)."""
+        num_rays, num_samples = ray_samples.positions.shape[:2]
+        positions = ray_samples.positions.reshape(-1, 3)
+        if self.model.use_view:
+            raw = self.model(positions, ray_samples.view_directions.reshape(-1, 3))
+        else:
+            raw = self.model(positions)
+        raw = raw.reshape(num_rays, num_samples, 4)
+        color = torch.sigmoid(raw[..., :3])
+        opacity = F.softplus(raw[..., 3])
+        assert not color.isnan().any()
+        assert not opacity.isnan().any()
+        weights = blend_weights_torch(ray_samples.t_values, opacity)
+        out_color = (weights.unsqueeze(-1) * color).sum(-2)
+        weights = weights[:, :-1]
+        out_alpha = weights.sum(-1)
+        out_depth = None
+        if include_depth:
+            cutoff = weights.argmax(-1)
+            cutoff[out_alpha < .1] = -1
+            out_depth = ray_samples.t_values[torch.arange(num_rays), cutoff]
+        return RenderResult(out_color, out_alpha, out_depth)
+
+    def _loss(self, step: int, dataset, batch: List[int]) -> torch.Tensor:
+        device = next(self.model.parameters()).device
+        rays = dataset.get_rays(batch, step).to(device)
+        return dataset.loss(step, rays, self.render(rays, True))
+
+    # ---- inference --------------------------------------------------------------------
+    def batched_render(self, samples: RaySamples, batch_size: int, include_depth: bool) -> RenderResult:
+        """Render in ray batches; returns numpy arrays (ray_caster.py:103-138).  Results stay on
+        the device until the end: one device->host copy per call instead of one per batch."""
+        self.model.eval()
+        colors, alphas, depths = [], [], []
+        with torch.no_grad():
+            device = next(self.model.parameters()).device
+            num_rays = samples.num_rays if isinstance(samples, RayBundle) else len(samples.positions)
+            for start in range(0, num_rays, batch_size):
+                end = min(start + batch_size, num_rays)
+                batch = samples.subset(range(start, end)) if isinstance(samples, RayBundle) \
+                    else samples.subset(list(range(start, end)))
+                pred = self.render(batch.to(device), include_depth)
+                colors.append(pred.color)
+                alphas.append(pred.alpha)
+                if include_depth:
+                    depths.append(pred.depth)
+            self.check_nan()
+        self.model.train()
+        return RenderResult(torch.cat(colors).cpu().numpy(), torch.cat(alphas).cpu().numpy(),
+                            torch.cat(depths).cpu().numpy() if include_depth else None)
+
+    def render_image(self, sampler: RaySampler, index: int, batch_size: int,
+                     color_space="RGB") -> np.ndarray:
+        """Render camera ``index % num_cameras`` to an (H,W,3) uint8 image."""
+        camera = index % sampler.num_cameras
+        samples = sampler.rays_for_camera(camera)
+        pred = self.batched_render(samples, batch_size, False)
+        return sampler.to_image(camera, pred.color, color_space)
+
+    # ---- training driver (ray_caster.py:220-376) --------------------------------------------
+    def _validate(self, dataset, batch_size: int, step: int) -> float:
+        num_rays = len(dataset)
+        num_validate = min(num_rays, 1024 * 100)
+        if num_validate < num_rays:
+            val_index = np.linspace(0, num_rays, num_validate, endpoint=False).astype(np.int32)
+            val_index = dataset.to_valid(val_index.tolist())
+        else:
+            val_index = np.arange(num_rays)
+        self.model.eval()
+        losses = []
+        with torch.no_grad():
+            for start in range(0, num_validate, batch_size):
+                if start + batch_size > len(val_index):
+                    break
+                losses.append(self._loss(step, dataset, val_index[start:start + batch_size]))
+        self.model.train()
+        loss = torch.stack(losses).mean().item() if losses else float("nan")
+        return -10. * np.log10(loss)
+
+    def fit(self, train_dataset, val_dataset, batch_size: int, learning_rate: float,
+            num_steps: int, crop_steps: int, report_interval: int, decay_rate: float,
+            decay_steps: int, weight_decay: float, visualizers: List, disable_aml=False,
+            grad_sync=None) -> List[LogEntry]:
+        """Adam + value/norm clipping + exponential LR decay, as ray_caster.py:248-376.
+        ``grad_sync`` (optional) is called between backward and clipping -- the data-parallel
+        gradient all-reduce hook (``parallel.allreduce_gradients``)."""
+        from .ray_dataset_modes import Mode
+        trainval = train_dataset.sample_cameras(val_dataset.num_cameras, val_dataset.num_samples, False)
+        optim = torch.optim.Adam(self.model.parameters(), learning_rate, weight_decay=weight_decay)
+        step, epoch, log = 0, 0, []
+        start_time = time.time()
+        dataset_mode = train_dataset.mode
+        for ds in (train_dataset, val_dataset, trainval):
+            ds.mode = Mode.Center if crop_steps else dataset_mode
+
+        def render_image(samples, include_depth):
+            return self.batched_render(samples, batch_size, include_depth)
+
+        def render_act(sampler, camera):
+            raise NotImplementedError("activation rendering is lecture visualisation (out of scope)")
+
+        while step <= num_steps:
+            num_rays = len(train_dataset)
+            index = np.arange(num_rays)
+            np.random.shuffle(index)
+            for start in range(0, num_rays, batch_size):
+                if step > num_steps:
+                    break
+                exponential_lr_decay(optim, learning_rate, step, decay_rate, decay_steps)
+                batch = index[start:min(start + batch_size, num_rays)].tolist()
+                optim.zero_grad()
+                loss = self._loss(step, train_dataset, batch)
+                loss.backward()
+                if grad_sync is not None:
+                    grad_sync(self.model)
+                torch.nn.utils.clip_grad_value_(self.model.parameters(), 0.1)
+                torch.nn.utils.clip_grad_norm_(self.model.parameters(), 0.1)
+                optim.step()
+
+                if step < 10 or step % report_interval == 0:
+                    epoch += 1
+                    train_psnr = self._validate(trainval, batch_size, step)
+                    val_psnr = self._validate(val_dataset, batch_size, step)
+                    now = time.time()
+                    if step >= report_interval:
+                        time_per_step = (now - start_time) / step
+                        eta = time.strftime("%a, %d %b %Y %H:%M:%S +0000",
+                                            time.gmtime(now + (num_steps - step) * time_per_step))
+                    else:
+                        time_per_step, eta = 0, "N/A"
+                    print("{:07}".format(step), "{:2f} s/step".format(time_per_step),
+                          "psnr_train: {:2f}".format(train_psnr), "val_psnr: {:2f}".format(val_psnr),
+                          "lr: {:.2e}".format(optim.param_groups[0]["lr"]), "eta:", eta)
+                    if step % report_interval == 0:
+                        log.append(LogEntry(step, now - start_time,
+                                            copy.deepcopy(self.model.state_dict()), train_psnr, val_psnr))
+                    if train_dataset.mode == Mode.Center and step >= crop_steps:
+                        print("Removing center crop...")
+                        for ds in (train_dataset, val_dataset, trainval):
+                            ds.mode = dataset_mode
+                        step += 1
+                        break
+                for visualizer in visualizers:
+                    visualizer.visualize(step, render_image, render_act)
+                step += 1
+        return log

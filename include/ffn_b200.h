@@ -1,0 +1,131 @@
+/*
+ * ffn_b200.h -- C ABI of libffn_b200.so: the B200 (sm_100a) volume-rendering hot path
+ * that replaces, for matajoh/fourier_feature_nets,
+ *
+ *     RaySampler.sample            fourier_feature_nets/ray_sampler.py:359-403
+ *  -> NeRF.forward                 fourier_feature_nets/nerf_model.py:86-124
+ *     FourierFeatureMLP.forward    fourier_feature_nets/fourier_feature_models.py:57-78
+ *  -> Raycaster.render             fourier_feature_nets/ray_caster.py:48-93
+ *     calculate_blend_weights      fourier_feature_nets/utils.py:72-97
+ *
+ * The reference has no FFI of its own (pure Python); these entry points sit one level
+ * below its Python seams and are what a ctypes binding in the
+ * reference would call (INTEGRATION.md shows that binding).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every data pointer is a DEVICE pointer on the
+ *    current CUDA device, contiguous row-major float32, 16-byte aligned;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *    synchronises;
+ *  - return 0 on success, non-zero on error; ffn_last_error() gives the message
+ *    (thread-local);
+ *  - the library owns only what lives inside an ffn_net_t handle.
+ */
+#ifndef FFN_B200_H_
+#define FFN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFN_B200_VERSION 100
+
+/* operand type fed to the tensor cores (accumulation, bias, activations, encodings,
+ * heads and compositing are always float32) */
+#define FFN_OPERAND_FP16 0
+#define FFN_OPERAND_BF16 1
+
+#define FFN_MAX_LAYERS 16
+#define FFN_MAX_FREQS 10
+
+typedef struct ffn_net ffn_net_t;
+
+/* NeRF(num_layers, num_channels, max_log_scale_pos, num_freq_pos, max_log_scale_view,
+ *      num_freq_view, skips, include_inputs)   -- nerf_model.py:12-75.
+ * freq_pos / freq_view are the diagonal of the module's frozen pos_encoding /
+ * view_encoding buffers (2**linspace(0, max_log_scale, F), nerf_model.py:77-84). */
+typedef struct {
+  int32_t num_layers;
+  int32_t num_channels;      /* must be 256 (hidden_view = 128) */
+  int32_t num_freq_pos;      /* <= 10 */
+  int32_t num_freq_view;     /* <= 10 */
+  int32_t include_inputs;
+  int32_t num_skips;
+  int32_t skips[FFN_MAX_LAYERS];
+  float freq_pos[FFN_MAX_FREQS];
+  float freq_view[FFN_MAX_FREQS];
+  int32_t operand_dtype;     /* FFN_OPERAND_* */
+} ffn_nerf_desc_t;
+
+int ffn_version(void);
+const char* ffn_last_error(void);
+
+/* Build a handle for a NeRF of the given shape (allocates the packed-weight arena). */
+int ffn_nerf_create(const ffn_nerf_desc_t* desc, ffn_net_t** out);
+
+/* FourierFeatureMLP(num_inputs=3, num_outputs=4, a_values, b_values, layer_channels=[256]*n)
+ * -- fourier_feature_models.py:13-55.  a_values (E) / b_values (3,E) are HOST pointers
+ * (frozen buffers); NULL = the un-encoded MLP preset.  E <= 256. */
+int ffn_ffmlp_create(int32_t num_hidden_layers, int32_t num_channels, int32_t embedding_size,
+                     const float* a_values_host, const float* b_values_host,
+                     int32_t operand_dtype, ffn_net_t** out);
+
+void ffn_net_destroy(ffn_net_t* net);
+
+/* Number of (weight, bias) pairs ffn_net_pack expects and their order:
+ * NeRF: layers.0 .. layers.{L-1}, opacity_out, bottleneck, hidden_view, color_out.
+ * FourierFeatureMLP: layers.0 .. layers.{n}. */
+int ffn_net_num_linear(const ffn_net_t* net);
+
+/* Re-pack torch-layout (out,in) float32 weights + biases (device pointers, given as HOST
+ * arrays of pointers) into the tensor-core layout.  Call after every optimiser step. */
+int ffn_net_pack(ffn_net_t* net, const float* const* weights, const float* const* biases,
+                 void* stream);
+
+/* model(positions[, views]) -> (N,4) raw [rgb | sigma]   (nerf_model.py:86, ray_caster.py:61-66) */
+int ffn_mlp_forward(ffn_net_t* net, const float* positions, const float* views, int64_t n,
+                    float* out4, void* stream);
+
+/* Raycaster.render on materialised RaySamples (ray_caster.py:48-93):
+ * positions (R,S,3), view_directions (R,S,3) or NULL, t_values (R,S)
+ * -> color (R,3), alpha (R), depth (R) or NULL.  nan_flag: device int, OR-ed with 1 when a
+ * NaN colour/opacity is produced (the reference's asserts at ray_caster.py:73-74). */
+int ffn_render_samples(ffn_net_t* net, const float* positions, const float* view_directions,
+                       const float* t_values, int64_t num_rays, int32_t num_samples,
+                       float* color, float* alpha, float* depth, int32_t* nan_flag, void* stream);
+
+/* RaySampler.sample (no focus sampling) fused into the render:
+ * starts (R,3), directions (R,3), near (R), far (R) [already annealed, ray_sampler.py:373-378],
+ * lin = torch.linspace(0,1,S) (S floats), jitter (R,S) uniform draws or NULL.
+ * stratified != 0 with jitter == NULL draws Philox(seed, ray_offset + ray, sample) in-kernel. */
+int ffn_render_rays(ffn_net_t* net, const float* starts, const float* directions,
+                    const float* near, const float* far, const float* lin, const float* jitter,
+                    int32_t stratified, uint64_t seed, int64_t ray_offset, int64_t num_rays,
+                    int32_t num_samples, float* color, float* alpha, float* depth,
+                    float* t_values_out /* (R,S) or NULL */, int32_t* nan_flag, void* stream);
+
+/* Compositing alone (ray_caster.py:67-93 + utils.py:72-97) for any S:
+ * raw (R,S,4), t_values (R,S) -> color, alpha, depth (or NULL), weights (R,S) (or NULL). */
+int ffn_composite(const float* raw, const float* t_values, int64_t num_rays, int32_t num_samples,
+                  float* color, float* alpha, float* depth, float* weights, int32_t* nan_flag,
+                  void* stream);
+
+/* calculate_blend_weights(t_values (R,S), opacity (R,S)) -> weights (R,S)   (utils.py:72-97) */
+int ffn_blend_weights(const float* t_values, const float* opacity, int64_t num_rays,
+                      int32_t num_samples, float* weights, void* stream);
+
+/* Debug: dump the float32 post-activation output of MMA layer `layer` (row-major (N,256))
+ * for the first `n` points.  Used by the bring-up tests only. */
+int ffn_debug_layer(ffn_net_t* net, const float* positions, const float* views, int64_t n,
+                    int32_t layer, float* out256, void* stream);
+
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t ffn_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFN_B200_H_ */

@@ -25,7 +25,7 @@ import numpy as np
 __all__ = [
     "torch_linspace", "linspace", "calculate_blend_weights", "determine_cdf",
     "sample_t_values", "unproject", "raycast", "near_far", "sample_rays",
-    "nerf_encoding_matrix", "nerf_forward", "positional_b_values",
+    "nerf_encoding_matrix", "nerf_forward", "nerf_hidden", "positional_b_values",
     "ffmlp_forward", "render", "render_rays", "softplus", "sigmoid",
     "OracleSamples", "OracleRender", "nerf_param_shapes", "init_nerf_params",
     "init_ffmlp_params", "image_loss",
@@ -349,6 +349,35 @@ def nerf_forward(params: Dict[str, np.ndarray], position: np.ndarray, view: np.n
     out = np.maximum(_linear(out, params["hidden_view.weight"], params["hidden_view.bias"]), 0)
     color = _linear(out, params["color_out.weight"], params["color_out.bias"])
     return np.concatenate([color, opacity], -1).astype(dtype)
+
+
+def nerf_hidden(params: Dict[str, np.ndarray], position: np.ndarray, view: np.ndarray,
+                num_layers=8, max_log_scale_pos=9.0, num_freq_pos=10,
+                max_log_scale_view=3.0, num_freq_view=4, skips=(4,),
+                include_inputs=True) -> List[np.ndarray]:
+    """Post-activation outputs of every dense layer of nerf_model.py:111-122 in order:
+    layers.0..L-1 (ReLU), bottleneck (linear), hidden_view (ReLU).  Bring-up aid."""
+    dtype = position.dtype
+    skips = set(skips)
+    pos_enc = nerf_encoding_matrix(max_log_scale_pos, num_freq_pos, 3, dtype)
+    view_enc = nerf_encoding_matrix(max_log_scale_view, num_freq_view, 3, dtype)
+    e = (position @ pos_enc).astype(dtype)
+    enc_p = np.concatenate([np.cos(e), np.sin(e)] + ([position] if include_inputs else []), -1)
+    e = (view @ view_enc).astype(dtype)
+    enc_v = np.concatenate([np.cos(e), np.sin(e)] + ([view] if include_inputs else []), -1)
+    outs = []
+    out = enc_p
+    for i in range(num_layers):
+        if i in skips:
+            out = np.concatenate([out, enc_p], -1)
+        out = np.maximum(_linear(out, params[f"layers.{i}.weight"], params[f"layers.{i}.bias"]), 0)
+        outs.append(out)
+    b = _linear(out, params["bottleneck.weight"], params["bottleneck.bias"])
+    outs.append(b)
+    out = np.maximum(_linear(np.concatenate([b, enc_v], -1), params["hidden_view.weight"],
+                             params["hidden_view.bias"]), 0)
+    outs.append(out)
+    return outs
 
 
 def ffmlp_forward(params: Dict[str, np.ndarray], inputs: np.ndarray,
