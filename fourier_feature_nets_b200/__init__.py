@@ -8,6 +8,7 @@ render/training path: ``Raycaster``, ``RaySampler``, ``RaySamples``, ``NeRF``,
 from .camera_info import CameraInfo, Resolution
 from .fourier_feature_models import (BasicFourierMLP, FourierFeatureMLP, GaussianFourierMLP, MLP,
                                      PositionalFourierMLP)
+from .image_dataset import ImageDataset, RayDataset
 from .nerf_model import NeRF
 from .ray_caster import Raycaster
 from .ray_dataset_modes import Mode
@@ -21,5 +22,5 @@ __version__ = "0.1.0"
 
 __all__ = ["CameraInfo", "Resolution", "MLP", "NeRF", "BasicFourierMLP", "FourierFeatureMLP",
            "PositionalFourierMLP", "GaussianFourierMLP", "Raycaster", "RayCaster", "RaySampler",
-           "RaySamples", "RayBundle", "RenderResult", "Mode", "calculate_blend_weights",
+           "RaySamples", "RayBundle", "RenderResult", "Mode", "ImageDataset", "RayDataset", "calculate_blend_weights",
            "exponential_lr_decay", "linspace", "load_model", "orbit", "__version__"]

@@ -585,6 +585,7 @@ static int launch_composite(const float* raw, const float* t, long long R, int S
 
 extern "C" int ffn_mlp_forward(ffn_net_t* net, const float* positions, const float* views, int64_t n,
                                float* out4, void* stream) {
+  if (net && n == 0) return 0;
   if (!net || !positions || !out4) return fail("ffn_mlp_forward: null argument");
   if (net->use_view && !views) return fail("ffn_mlp_forward: this model needs view directions");
   KernelArgs ka;
@@ -607,6 +608,7 @@ extern "C" int ffn_debug_layer(ffn_net_t* net, const float* positions, const flo
 extern "C" int ffn_render_samples(ffn_net_t* net, const float* positions, const float* view_directions,
                                   const float* t_values, int64_t R, int32_t S, float* color,
                                   float* alpha, float* depth, int32_t* nan_flag, void* stream_) {
+  if (net && R == 0) return 0;
   if (!net || !positions || !t_values || !color || !alpha || !nan_flag)
     return fail("ffn_render_samples: null argument");
   if (net->use_view && !view_directions) return fail("ffn_render_samples: this model needs view directions");
@@ -631,6 +633,7 @@ extern "C" int ffn_render_rays(ffn_net_t* net, const float* starts, const float*
                                const float* jitter, int32_t stratified, uint64_t seed,
                                int64_t ray_offset, int64_t R, int32_t S, float* color, float* alpha,
                                float* depth, float* t_out, int32_t* nan_flag, void* stream_) {
+  if (net && R == 0) return 0;
   if (!net || !starts || !directions || !near_ || !far_ || !lin || !color || !alpha || !nan_flag)
     return fail("ffn_render_rays: null argument");
   if (S < 1) return fail("ffn_render_rays: num_samples must be >= 1");
@@ -658,6 +661,7 @@ extern "C" int ffn_render_rays(ffn_net_t* net, const float* starts, const float*
 extern "C" int ffn_composite(const float* raw, const float* t_values, int64_t R, int32_t S, float* color,
                              float* alpha, float* depth, float* weights, int32_t* nan_flag,
                              void* stream) {
+  if (R == 0) return 0;
   if (!raw || !t_values) return fail("ffn_composite: null argument");
   if (S < 1) return fail("ffn_composite: num_samples must be >= 1");
   return launch_composite(raw, t_values, R, S, color, alpha, depth, weights, nan_flag, (cudaStream_t)stream);
@@ -665,6 +669,7 @@ extern "C" int ffn_composite(const float* raw, const float* t_values, int64_t R,
 
 extern "C" int ffn_blend_weights(const float* t_values, const float* opacity, int64_t R, int32_t S,
                                  float* weights, void* stream) {
+  if (R == 0) return 0;
   if (!t_values || !opacity || !weights) return fail("ffn_blend_weights: null argument");
   if (S < 1) return fail("ffn_blend_weights: num_samples must be >= 1");
   if (R <= 0) return 0;

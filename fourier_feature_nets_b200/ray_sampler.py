@@ -29,8 +29,8 @@ class RaySamples(NamedTuple("RaySamples", [("positions", torch.Tensor),
     """Point samples ``start + direction * t`` grouped by ray: positions (R,S,3),
     view_directions (R,S,3), t_values (R,S), rays (R,) indices."""
 
-    def to(self, *args) -> "RaySamples":
-        return RaySamples(*[None if t is None else t.to(*args) for t in self])
+    def to(self, *args, **kwargs) -> "RaySamples":
+        return RaySamples(*[None if t is None else t.to(*args, **kwargs) for t in self])
 
     def pin_memory(self) -> "RaySamples":
         return RaySamples(*[None if t is None else t.pin_memory() for t in self])
@@ -103,8 +103,8 @@ class RayBundle(RaySamples):
                          None if self.rays is None else fn(self.rays), self.num_samples,
                          self.stratified, None if self.jitter is None else fn(self.jitter), self.seed)
 
-    def to(self, *args) -> "RayBundle":
-        return self._map(lambda t: t.to(*args))
+    def to(self, *args, **kwargs) -> "RayBundle":
+        return self._map(lambda t: t.to(*args, **kwargs))
 
     def pin_memory(self) -> "RayBundle":
         return self._map(lambda t: t.pin_memory())
@@ -157,6 +157,9 @@ class RaySampler:
         self.batch_size = batch_size
         self.seed = 20080524
         self._draws = 0
+        # True: stratified jitter is drawn inside the kernel (Philox); False: on the host with
+        # torch.rand like the reference (ray_sampler.py:383).  None = decide by table residency.
+        self.device_jitter = None
 
         xs, ys = np.meshgrid(np.arange(self.image_width), np.arange(self.image_height))
         self.points = np.stack([xs, ys], -1).reshape(-1, 2)
@@ -305,7 +308,8 @@ class RaySampler:
 
         if not self.focus_sampling:
             jitter = None
-            if self.stratified and not starts.is_cuda:
+            on_device = starts.is_cuda if self.device_jitter is None else self.device_jitter
+            if self.stratified and not on_device:
                 # host path keeps the reference's RNG stream (ray_sampler.py:383)
                 jitter = torch.rand((n, self.num_samples), dtype=torch.float32)
             self._draws += 1

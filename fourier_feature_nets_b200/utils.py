@@ -21,8 +21,8 @@ class RenderResult(NamedTuple("RenderResult", [("color", torch.Tensor),
     def device(self) -> torch.device:
         return self.color.device
 
-    def to(self, *args) -> "RenderResult":
-        return RenderResult(*[None if t is None else t.to(*args) for t in self])
+    def to(self, *args, **kwargs) -> "RenderResult":
+        return RenderResult(*[None if t is None else t.to(*args, **kwargs) for t in self])
 
     def numpy(self) -> "RenderResult":
         return RenderResult(*[None if t is None else t.cpu().numpy() for t in self])

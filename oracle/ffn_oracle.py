@@ -428,14 +428,20 @@ def render(color_o: np.ndarray, t_values: np.ndarray, include_depth: bool = True
 
 
 def render_rays(model_fn, samples: OracleSamples, include_depth: bool = True,
-                use_view: bool = True) -> OracleRender:
+                use_view: bool = True, chunk: int = 8192) -> OracleRender:
     """ray_caster.py:48-93: flatten -> model -> reshape -> ``render``."""
     R, S = samples.positions.shape[:2]
     pos = samples.positions.reshape(-1, 3)
-    if use_view:
-        color_o = model_fn(pos, samples.view_directions.reshape(-1, 3))
-    else:
-        color_o = model_fn(pos)
+    views = samples.view_directions.reshape(-1, 3)
+    # the model is evaluated in row chunks that fit the CPU caches (the result does not
+    # depend on the chunking: every row is independent)
+    outs = []
+    for lo in range(0, len(pos), chunk):
+        if use_view:
+            outs.append(model_fn(pos[lo:lo + chunk], views[lo:lo + chunk]))
+        else:
+            outs.append(model_fn(pos[lo:lo + chunk]))
+    color_o = np.concatenate(outs, 0)
     return render(color_o.reshape(R, S, 4), samples.t_values, include_depth)
 
 

@@ -240,6 +240,43 @@ def main():
         t_values=fsamp.t_values.numpy(), positions=fsamp.positions.numpy(),
         t_det=fsamp_det.t_values.numpy())
 
+    # ---- ImageDataset: index tables, GT lookup, loss (image_dataset.py) ----------------
+    rng = np.random.default_rng(11)
+    res2 = 20
+    dcams = [look_at_camera(ffn, "d%d" % i, p, res2) for i, p in enumerate(
+        [(0, 0, -4), (4, 0.5, 0.3), (-2.5, 1.5, 2.8), (0.3, 3.9, 0.2), (2, -2, 2.5)])]
+    imgs = rng.integers(0, 256, size=(5, res2, res2, 4), dtype=np.uint8)
+    yy, xx = np.mgrid[:res2, :res2]
+    for i in range(5):      # alpha: a disc, zero outside
+        imgs[i, ..., 3] = np.where((xx - 10 - i) ** 2 + (yy - 9) ** 2 < 30, imgs[i, ..., 3] | 1, 0)
+    ds = ffn.ImageDataset("train", imgs, bounds, dcams, 16, True, True, None, 4096, "RGB", 6, 0.2, 0)
+    out = {"images": imgs, "bounds": bounds,
+           "intrinsics": np.stack([c.intrinsics for c in dcams]),
+           "extrinsics": np.stack([c.extrinsics for c in dcams]),
+           "crop_index": ds.crop_index.numpy(), "sparse_index": ds.sparse_index.numpy(),
+           "dilate_index": ds.dilate_index.numpy(), "dilate_ranges": np.array(ds.dilate_ranges),
+           "colors": ds.colors.numpy(), "alphas": ds.alphas.numpy()}
+    batch = rng.integers(0, 5 * res2 * res2, size=200).tolist()
+    for mode in ("Full", "Center", "Sparse", "Dilate"):
+        ds.mode = getattr(ffn.RayDataset.Mode, mode)
+        b = [i % len(ds) for i in batch]
+        torch.manual_seed(5)
+        rays = ds.get_rays(b, 3)
+        fake = ffn.utils.RenderResult(torch.rand(len(rays.rays), 3, generator=torch.Generator().manual_seed(1)),
+                                      torch.rand(len(rays.rays), generator=torch.Generator().manual_seed(2)), None)
+        out["len_" + mode] = np.array(len(ds))
+        out["batch_" + mode] = np.array(b)
+        out["rays_" + mode] = rays.rays.numpy()
+        out["loss_" + mode] = ds.loss(3, rays, fake).numpy()
+        out["fake_color_" + mode] = fake.color.numpy()
+        out["fake_alpha_" + mode] = fake.alpha.numpy()
+        out["index_cam2_" + mode] = np.array(ds.index_for_camera(2))
+        out["rays_cam2_" + mode] = ds.rays_for_camera(2).rays.numpy()
+    ds.mode = ffn.RayDataset.Mode.Full
+    sub = ds.sample_cameras(3, 16, False)
+    out["sample_cameras_names"] = np.array([c.name for c in sub.cameras])
+    np.savez_compressed(os.path.join(HERE, "dataset.npz"), **out)
+
     # ---- known-answer: docs/ray_data.tsv -----------------------------------
     tsv = np.loadtxt(os.path.join(REF, "docs", "ray_data.tsv"), skiprows=1, dtype=np.float64)
     np.savez_compressed(os.path.join(HERE, "ray_data_kat.npz"),
