@@ -100,7 +100,7 @@ def lib() -> ctypes.CDLL:
 EXPORTED_SYMBOLS = [
     "ffn_version", "ffn_last_error", "ffn_nerf_create", "ffn_ffmlp_create", "ffn_net_destroy",
     "ffn_net_num_linear", "ffn_net_pack", "ffn_mlp_forward", "ffn_render_samples",
-    "ffn_render_rays", "ffn_composite", "ffn_blend_weights", "ffn_debug_layer", "ffn_launch_count",
+    "ffn_render_rays", "ffn_composite", "ffn_blend_weights", "ffn_debug_layer", "ffn_debug_stats", "ffn_launch_count",
 ]
 
 
@@ -260,6 +260,12 @@ class Net:
                                          _ptr(depth), _ptr(t_out), _ptr(self._nan_flag), _stream()),
                    "ffn_render_rays")
         return color, alpha, depth, t_out
+
+    def debug_stats(self):
+        out = (ctypes.c_uint64 * 8)()
+        lib().ffn_debug_stats.argtypes = [c_void_p, c_void_p]
+        _check(lib().ffn_debug_stats(self.handle, out), "ffn_debug_stats")
+        return list(out)
 
     def nan_flag(self) -> int:
         """Read (and clear) the device NaN flag -- one D2H sync."""

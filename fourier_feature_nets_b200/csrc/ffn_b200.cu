@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -41,7 +42,8 @@ struct PackLayer {          // how one MMA layer's weights are gathered from a t
   int n_chunks;
   int colmap_off;           // offset into the colmap array (n_chunks * 64 entries)
   uint32_t w_offset;        // byte offset in the packed arena
-  int bias_row;
+  uint32_t bias_off;        // byte offset of the bias tile in the packed arena
+  int bias_row;             // >= 0: this MMA layer carries the Linear's bias
 };
 struct PackHead {           // a small output head evaluated on CUDA cores in fp32
   int linear, in_features, first_out, n_out;
@@ -64,6 +66,7 @@ struct ffn_net {
   ConstParams* d_cparams = nullptr;
   float* d_ffm_b = nullptr;
   float* d_ffm_a = nullptr;
+  unsigned long long* d_stats = nullptr;   // issuer-warp cycle counters (FFN_STATS=1)
   float* d_scratch = nullptr;   // grow-only temp (raw outputs for the non-fused path)
   size_t scratch_bytes = 0;
   long long gen = 0;            // bumped by every pack
@@ -87,6 +90,7 @@ struct PackArgs {
   int n_chunks[kMaxMmaLayers];
   int colmap_off[kMaxMmaLayers];
   uint32_t w_offset[kMaxMmaLayers];
+  uint32_t bias_off[kMaxMmaLayers];
   int bias_row[kMaxMmaLayers];
   int n_heads;
   int head_linear[4], head_in[4], head_first[4], head_n[4];
@@ -125,13 +129,25 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs pa, const i
   }
 }
 
-__global__ void pack_const_kernel(const __grid_constant__ PackArgs pa, ConstParams* __restrict__ cp) {
+// bias tiles (B operand of the bias UMMA, layout in ffn_common.cuh) + head weights in ConstParams
+template <bool kBF16>
+__global__ void pack_const_kernel(const __grid_constant__ PackArgs pa, ConstParams* __restrict__ cp,
+                                  uint8_t* __restrict__ wpack) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nth = gridDim.x * blockDim.x;
   for (int l = 0; l < pa.n_layers; ++l) {
     if (pa.bias_row[l] < 0) continue;
     const float* b = pa.b[pa.linear[l]];
-    for (int i = tid; i < 256; i += nth) cp->bias[pa.bias_row[l]][i] = i < pa.n[l] ? b[i] : 0.f;
+    for (int n = tid; n < pa.n[l]; n += nth) {
+      const float v = b[n];
+      float hi;
+      if constexpr (kBF16) hi = __bfloat162float(__float2bfloat16_rn(v));
+      else hi = __half2float(__float2half_rn(v));
+      // element (n,0) = hi part, (n,1) = residual; the rest of the tile stays zero (memset at create)
+      const uint32_t pk = ptx::pack2<kBF16, false>(hi, v - hi);
+      *reinterpret_cast<uint32_t*>(wpack + pa.bias_off[l] + (size_t)(n >> 3) * kBiasTileSBO +
+                                   (size_t)(n & 7) * 16) = pk;
+    }
   }
   for (int h = 0; h < pa.n_heads; ++h) {
     const float* w = pa.w[pa.head_linear[h]];
@@ -274,13 +290,22 @@ static int finalize_net(ffn_net* net) {
     net->layers[l].w_offset = off;
     off += (uint32_t)net->layers[l].n * 128u * (uint32_t)net->layers[l].n_chunks;
   }
+  for (int l = 0; l < net->num_layers; ++l) {
+    const bool has_bias = net->pack_layers[l].bias_row >= 0;
+    net->layers[l].has_bias = has_bias ? 1 : 0;
+    net->layers[l].bias_off = net->pack_layers[l].bias_off = off;
+    if (has_bias) off += (uint32_t)net->layers[l].n * 32u;
+  }
   net->wpack_bytes = off;
   CUDA_TRY(cudaMalloc(&net->d_wpack, net->wpack_bytes));
+  CUDA_TRY(cudaMemset(net->d_wpack, 0, net->wpack_bytes));
   CUDA_TRY(cudaMalloc(&net->d_colmap, net->colmap_host.size() * sizeof(int)));
   CUDA_TRY(cudaMemcpy(net->d_colmap, net->colmap_host.data(), net->colmap_host.size() * sizeof(int),
                       cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&net->d_cparams, sizeof(ConstParams)));
   CUDA_TRY(cudaMemset(net->d_cparams, 0, sizeof(ConstParams)));
+  CUDA_TRY(cudaMalloc(&net->d_stats, 8 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(net->d_stats, 0, 8 * sizeof(unsigned long long)));
   if (g_num_sms == 0) {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -491,7 +516,7 @@ extern "C" int ffn_ffmlp_create(int32_t num_hidden, int32_t num_channels, int32_
 extern "C" void ffn_net_destroy(ffn_net_t* net) {
   if (!net) return;
   cudaFree(net->d_wpack); cudaFree(net->d_colmap); cudaFree(net->d_cparams);
-  cudaFree(net->d_ffm_a); cudaFree(net->d_ffm_b); cudaFree(net->d_scratch);
+  cudaFree(net->d_ffm_a); cudaFree(net->d_ffm_b); cudaFree(net->d_scratch); cudaFree(net->d_stats);
   delete net;
 }
 
@@ -512,7 +537,7 @@ extern "C" int ffn_net_pack(ffn_net_t* net, const float* const* weights, const f
     const PackLayer& pl = net->pack_layers[l];
     pa.linear[l] = pl.linear; pa.in_features[l] = pl.in_features; pa.n[l] = pl.n;
     pa.n_chunks[l] = pl.n_chunks; pa.colmap_off[l] = pl.colmap_off; pa.w_offset[l] = pl.w_offset;
-    pa.bias_row[l] = pl.bias_row;
+    pa.bias_row[l] = pl.bias_row; pa.bias_off[l] = pl.bias_off;
   }
   pa.n_heads = (int)net->heads.size();
   for (int h = 0; h < pa.n_heads; ++h) {
@@ -522,7 +547,8 @@ extern "C" int ffn_net_pack(ffn_net_t* net, const float* const* weights, const f
   dim3 grid(40, net->num_layers);
   if (net->bf16) pack_weights_kernel<true><<<grid, 256, 0, stream>>>(pa, net->d_colmap, net->d_wpack);
   else pack_weights_kernel<false><<<grid, 256, 0, stream>>>(pa, net->d_colmap, net->d_wpack);
-  pack_const_kernel<<<1, 256, 0, stream>>>(pa, net->d_cparams);
+  if (net->bf16) pack_const_kernel<true><<<1, 256, 0, stream>>>(pa, net->d_cparams, net->d_wpack);
+  else pack_const_kernel<false><<<1, 256, 0, stream>>>(pa, net->d_cparams, net->d_wpack);
   g_launches += 2;
   CUDA_TRY(cudaGetLastError());
   net->gen = g_gen.fetch_add(1);
@@ -548,6 +574,10 @@ static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream) {
   ka.f_pos = net->f_pos; ka.f_view = net->f_view; ka.include_inputs = net->include_inputs;
   ka.use_view = net->use_view; ka.emb = net->emb; ka.ffm_a = net->d_ffm_a; ka.ffm_b = net->d_ffm_b;
   ka.bf16 = net->bf16;
+  static const int env_dbg_flags = getenv("FFN_DBG_FLAGS") ? atoi(getenv("FFN_DBG_FLAGS")) : 0;
+  ka.dbg_flags = env_dbg_flags;
+  static const bool env_stats = getenv("FFN_STATS") != nullptr;
+  ka.stats = env_stats ? net->d_stats : nullptr;
   const long long tiles = (ka.M + kTileM - 1) / kTileM;
   if (tiles > 0x7fffffffLL) return fail("too many rows for one launch");
   ka.num_tiles = (int)tiles;
@@ -678,5 +708,13 @@ extern "C" int ffn_blend_weights(const float* t_values, const float* opacity, in
       t_values, opacity, R, S, weights);
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ffn_debug_stats(ffn_net_t* net, uint64_t* out8) {
+  if (!net || !out8) return fail("ffn_debug_stats: null argument");
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out8, net->d_stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemset(net->d_stats, 0, 8 * sizeof(unsigned long long)));
   return 0;
 }

@@ -48,8 +48,19 @@ struct LayerDesc {
   uint8_t bias_row;                        // row of ConstParams::bias
   uint8_t src[kMaxChunksPerLayer];         // A chunk index (0..3 act, 4 enc) per K-chunk
   uint8_t ksteps[kMaxChunksPerLayer];      // UMMA K-steps (of 16) per K-chunk
-  uint8_t head_n, pad0, pad1, pad2;     // EPI_RELU_HEAD: outputs 0..head_n-1
+  uint8_t head_n, has_bias, pad1, pad2;    // EPI_RELU_HEAD: outputs 0..head_n-1; has_bias: bias tile present
+  uint32_t bias_off;                       // byte offset of the packed bias tile (N x 32 B, see kBiasTile*)
 };
+
+// Bias is folded into the accumulator by one extra K=16 UMMA per layer:
+//   A = "ones" tile (every row [1,1,0,...,0]; 256 B in shared memory, all 16 row groups alias the same
+//       two 8x16B core matrices through a stride-byte-offset of 0),
+//   B = bias tile, K-major no-swizzle core matrices: B[n][0] = fp16(b_n), B[n][1] = fp16(b_n - B[n][0]).
+// byte offset of element (n, k) inside a bias tile:
+//   (n / 8) * kBiasTileSBO + (k / 8) * kBiasTileLBO + (n % 8) * 16 + (k % 8) * 2
+constexpr int kBiasTileLBO = 128;   // between the two K-adjacent 8x8 core matrices
+constexpr int kBiasTileSBO = 256;   // between N-adjacent core matrices (8-row groups)
+constexpr int kSmemOnes = kSmemMisc + 2816;   // 256-byte ones tile at the end of the misc region
 
 // encodings
 enum : int32_t { ENC_NERF = 0, ENC_FFMLP = 1, ENC_NONE = 2 };
@@ -57,11 +68,10 @@ enum : int32_t { ENC_NERF = 0, ENC_FFMLP = 1, ENC_NONE = 2 };
 // input modes
 enum : int32_t { MODE_POINTS = 0, MODE_SAMPLES = 1, MODE_RAYS = 2 };
 
-// Broadcast-read parameters: biases, head weights, frequency tables.  Lives in
+// Broadcast-read parameters: head weights (sigma / rgb / final layer) and frequency tables.  Lives in
 // __constant__ memory; re-uploaded (device-to-device, stream ordered) whenever the
 // active net or its weights change.
 struct ConstParams {
-  float bias[kMaxMmaLayers][256];
   float head_w[4][256];
   float head_b[4];
   float freq_pos[16];
@@ -103,7 +113,9 @@ struct KernelArgs {
   int32_t* nan_flag;
   // debug
   int32_t dbg_layer;
+  int32_t dbg_flags;           // bit 0: swap LBO/SBO roles of the no-swizzle descriptors (bring-up aid)
   float* dbg_out;              // (M,256)
+  unsigned long long* stats;   // optional [8]: issuer-warp cycle counters (FFN_STATS=1), see ffn_debug_stats
   int32_t num_tiles;
 };
 

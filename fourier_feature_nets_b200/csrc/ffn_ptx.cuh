@@ -136,6 +136,17 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// K-major operand WITHOUT swizzle: 8-row x 16-byte core matrices; `lbo` = byte offset between the two
+// K-adjacent core matrices of one K=16 step, `sbo` = byte offset between M/N-adjacent core matrices.
+__device__ __forceinline__ uint64_t make_kmajor_nosw_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  return d;
+}
+
 // Instruction descriptor for kind::f16: fp32 accumulate, K-major A and B, M = 128.
 //   [4,6) c_format (1 = f32)   [7,10) a_format   [10,13) b_format (0 = f16, 1 = bf16)
 //   [15] a_major  [16] b_major (0 = K)   [17,23) N >> 3   [24,29) M >> 4

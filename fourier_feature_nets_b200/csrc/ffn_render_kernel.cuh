@@ -148,6 +148,22 @@ __device__ __forceinline__ void write_enc_raw(uint32_t row_addr, uint32_t row7, 
   }
 }
 
+// 32 fp32 accumulator columns of one row -> 32 16-bit values -> four swizzled 16-byte units of the
+// row's 128-byte line in chunk `chunk_row` (u0 = index of the first unit: 0 or 4)
+template <bool kBF16, bool kRelu>
+__device__ __forceinline__ void store_act_block(const uint32_t (&v)[32], uint32_t chunk_row,
+                                                uint32_t row7, uint32_t u0) {
+#pragma unroll
+  for (uint32_t q = 0; q < 4; ++q) {
+    ptx::st_shared_v4(
+        chunk_row + (((u0 + q) ^ row7) << 4),
+        ptx::pack2<kBF16, kRelu>(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])),
+        ptx::pack2<kBF16, kRelu>(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
+        ptx::pack2<kBF16, kRelu>(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
+        ptx::pack2<kBF16, kRelu>(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
+  }
+}
+
 // ----------------------------------------------------------------------------------------
 // the kernel
 // ----------------------------------------------------------------------------------------
@@ -182,6 +198,13 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
     }
     ptx::fence_mbar_init();
   }
+  if (warp == 3) {
+    // "ones" A tile of the bias UMMA: two 8x16B core matrices; rows = [1,1,0,0,0,0,0,0] then zeros
+    const uint32_t one2 = ptx::pack2<kBF16, false>(1.f, 1.f);
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + kSmemOnes);
+    for (int i = lane; i < 64; i += 32) ones[i] = (i < 32 && (i & 3) == 0) ? one2 : 0u;
+    ptx::fence_proxy_async();
+  }
   if (warp == 2) {
     ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), 512);
     ptx::tmem_relinquish();
@@ -207,12 +230,15 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
         const LayerDesc& ld = args.layers[l];
         const uint32_t bytes = (uint32_t)ld.n * 128u;
         for (int s = 0; s < nslots; ++s) {
-          for (int c = 0; c < ld.n_chunks; ++c) {
+          // chunk -1 = the layer's bias tile (N x 32 B), then the weight K-chunks
+          for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
             ptx::mbar_wait(bar_w_empty + 8 * stage, phase ^ 1u);
             if (lane == 0) {
-              ptx::mbar_arrive_expect_tx(bar_w_full + 8 * stage, bytes);
-              ptx::bulk_g2s(smem_base + kSmemW + stage * kWStageBytes,
-                            args.wpack + ld.w_offset + (size_t)c * bytes, bytes,
+              const uint32_t nbytes = c < 0 ? (uint32_t)ld.n * 32u : bytes;
+              const uint8_t* src = c < 0 ? args.wpack + ld.bias_off
+                                         : args.wpack + ld.w_offset + (size_t)c * bytes;
+              ptx::mbar_arrive_expect_tx(bar_w_full + 8 * stage, nbytes);
+              ptx::bulk_g2s(smem_base + kSmemW + stage * kWStageBytes, src, nbytes,
                             bar_w_full + 8 * stage);
             }
             __syncwarp();
@@ -225,29 +251,43 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
     // ================================================================ UMMA issuer
     uint32_t stage = 0, phase = 0;
     uint32_t a_phase[2] = {0u, 0u};
+    const bool prof = args.stats != nullptr;
+    long long t_wait_a = 0, t_wait_w = 0, t_begin = prof ? clock64() : 0;
     for (int kp = 0; kp < my_tiles; kp += 2) {
       const int nslots = min(2, my_tiles - kp);
       for (int l = 0; l < L; ++l) {
         const LayerDesc& ld = args.layers[l];
         const uint32_t idesc = ptx::make_idesc_f16(ld.n, kBF16);
         for (int s = 0; s < nslots; ++s) {
+          long long t0 = prof ? clock64() : 0;
           ptx::mbar_wait(bar_a_ready + 8 * s, a_phase[s]);
+          if (prof) t_wait_a += clock64() - t0;
           a_phase[s] ^= 1u;
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)s * 256u;
           const uint32_t slot_base = smem_base + kSmemSlot0 + s * kSlotBytes;
           uint32_t accumulate = ld.accumulate;
-          for (int c = 0; c < ld.n_chunks; ++c) {
+          for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
+            t0 = prof ? clock64() : 0;
             ptx::mbar_wait(bar_w_full + 8 * stage, phase);
+            if (prof) t_wait_w += clock64() - t0;
             ptx::tc_fence_after();
             if (lane == 0) {
-              const uint32_t a_addr = slot_base + (uint32_t)ld.src[c] * kChunkBytesA;
               const uint32_t b_addr = smem_base + kSmemW + stage * kWStageBytes;
-              const int ks_n = ld.ksteps[c];
-              for (int ks = 0; ks < ks_n; ++ks) {
-                ptx::umma_f16(d_tmem, ptx::make_kmajor_sw128_desc(a_addr + ks * 32),
-                              ptx::make_kmajor_sw128_desc(b_addr + ks * 32), idesc, accumulate);
+              if (c < 0) {
+                // D = ones(128x16) . bias_tile(Nx16)^T : every row of the accumulator starts at the bias
+                const uint64_t a_desc = ptx::make_kmajor_nosw_desc(smem_base + kSmemOnes, 128u, 0u);
+                const uint64_t b_desc = ptx::make_kmajor_nosw_desc(b_addr, kBiasTileLBO, kBiasTileSBO);
+                ptx::umma_f16(d_tmem, a_desc, b_desc, idesc, accumulate);
                 accumulate = 1u;
+              } else {
+                const uint32_t a_addr = slot_base + (uint32_t)ld.src[c] * kChunkBytesA;
+                const int ks_n = ld.ksteps[c];
+                for (int ks = 0; ks < ks_n; ++ks) {
+                  ptx::umma_f16(d_tmem, ptx::make_kmajor_sw128_desc(a_addr + ks * 32),
+                                ptx::make_kmajor_sw128_desc(b_addr + ks * 32), idesc, accumulate);
+                  accumulate = 1u;
+                }
               }
               ptx::umma_commit(bar_w_empty + 8 * stage);   // frees the weight stage when the MMAs retire
               if (c == ld.n_chunks - 1) ptx::umma_commit(bar_acc_full + 8 * s);
@@ -257,6 +297,12 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           }
         }
       }
+    }
+    if (prof && lane == 0) {
+      atomicAdd(args.stats + 0, (unsigned long long)(clock64() - t_begin));
+      atomicAdd(args.stats + 1, (unsigned long long)t_wait_a);
+      atomicAdd(args.stats + 2, (unsigned long long)t_wait_w);
+      atomicAdd(args.stats + 3, 1ull);
     }
   } else if (warp >= 4) {
     // ================================================================ epilogue warpgroups
@@ -352,8 +398,40 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           // wide FourierFeatureMLP encodings: features [160, 256) -> act chunks 0..2
           write_enc_ffmlp<kBF16>(slot_base + row_off, row7, px, py, pz, args.ffm_b, args.ffm_a,
                                  args.emb, 160, 3);
+        } else if (ld.epi != EPI_RELU_HEAD && !ld.sigma_head && args.dbg_layer != l) {
+          // lean path (the bias is already in the accumulator): TMEM -> (ReLU) -> 16-bit pairs ->
+          // swizzled A tile; TMEM loads double-buffered against the conversion of the previous block
+          const int nblk = ld.n >> 5;
+          const uint32_t act_row = slot_base + row_off;
+          uint32_t va[32], vb[32];
+          ptx::tmem_ld32(taddr_base, va);
+          if (ld.epi == EPI_RELU_ACT) {
+#pragma unroll
+            for (int b = 0; b < 8; b += 2) {
+              if (b < nblk) {
+                ptx::tmem_wait_ld(va);
+                ptx::tmem_ld32(taddr_base + (uint32_t)(b + 1) * 32u, vb);
+                store_act_block<kBF16, true>(va, act_row + (b >> 1) * kChunkBytesA, row7, 0u);
+                ptx::tmem_wait_ld(vb);
+                if (b + 2 < nblk) ptx::tmem_ld32(taddr_base + (uint32_t)(b + 2) * 32u, va);
+                store_act_block<kBF16, true>(vb, act_row + (b >> 1) * kChunkBytesA, row7, 4u);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int b = 0; b < 8; b += 2) {
+              if (b < nblk) {
+                ptx::tmem_wait_ld(va);
+                ptx::tmem_ld32(taddr_base + (uint32_t)(b + 1) * 32u, vb);
+                store_act_block<kBF16, false>(va, act_row + (b >> 1) * kChunkBytesA, row7, 0u);
+                ptx::tmem_wait_ld(vb);
+                if (b + 2 < nblk) ptx::tmem_ld32(taddr_base + (uint32_t)(b + 2) * 32u, va);
+                store_act_block<kBF16, false>(vb, act_row + (b >> 1) * kChunkBytesA, row7, 4u);
+              }
+            }
+          }
         } else {
-          const float* __restrict__ bias = c_params.bias[ld.bias_row];
+          // general path: fp32 values are needed (sigma / rgb heads on CUDA cores, debug dump)
           const int nblk = ld.n >> 5;
           const bool relu = ld.epi != EPI_LINEAR_ACT;
           const bool to_act = ld.epi != EPI_RELU_HEAD;
@@ -367,7 +445,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
             float x[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float t = __uint_as_float(v[j]) + bias[c0 + j];
+              const float t = __uint_as_float(v[j]);
               x[j] = relu ? fmaxf(t, 0.f) : t;
             }
             if (ld.sigma_head) {

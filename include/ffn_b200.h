@@ -122,6 +122,11 @@ int ffn_blend_weights(const float* t_values, const float* opacity, int64_t num_r
 int ffn_debug_layer(ffn_net_t* net, const float* positions, const float* views, int64_t n,
                     int32_t layer, float* out256, void* stream);
 
+/* Debug: with FFN_STATS=1 in the environment the render kernel's UMMA-issuer warps accumulate
+ * {total cycles, cycles waiting for the epilogue, cycles waiting for weights, CTAs}; this reads
+ * (after a device sync) and clears them. */
+int ffn_debug_stats(ffn_net_t* net, uint64_t* out8);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t ffn_launch_count(void);
 

@@ -40,3 +40,8 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
 print("last launch %.3f ms -> %.2f M rays/s" % (ms, R / ms / 1e3))
+
+if os.environ.get("FFN_STATS"):
+    tot, wa, ww, n = eng.net.debug_stats()[:4]
+    print("issuer warp: total %.0f cyc/CTA, wait-epilogue %.1f%%, wait-weights %.1f%%, issuing %.1f%%" % (
+        tot / n, 100 * wa / tot, 100 * ww / tot, 100 * (tot - wa - ww) / tot))
