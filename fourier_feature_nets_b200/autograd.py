@@ -1,0 +1,203 @@
+"""Differentiable ``Raycaster.render`` on the CUDA kernels (training step).
+
+forward   ``ffn_train_forward``      fused sampling/encoding/MLP/compositing that also spills what the
+                                     backward needs: bf16 layer outputs, ReLU sign words, encoding rows,
+                                     raw network outputs and t values
+backward  ``ffn_composite_backward`` d(loss)/d(color, alpha) -> d(loss)/d(raw rgb, sigma) per sample
+          ``ffn_train_backward``     the dgrad chain on tcgen05 (transposed bf16 weights) -> dz per layer
+          weight gradients           dW = dz^T x : plain GEMMs over the saved tensors (cuBLAS through
+                                     ``torch.mm``), bias gradients = column sums
+
+Gradient operands are bf16 (fp32 accumulate); parity with the fp32 autograd of the reference definition is
+checked in tests/test_gpu_training.py (cosine >= 0.999, relative L2 error <= 3e-2 per parameter).
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_int32, c_int64, c_uint64, c_void_p
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+from . import engine as _engine
+
+
+def _bind(L):
+    if getattr(L, "_train_bound", False):
+        return
+    L.ffn_train_slots.argtypes = [c_void_p, ctypes.POINTER(c_int32), ctypes.POINTER(c_int32),
+                                  ctypes.POINTER(c_int32)]
+    L.ffn_net_pack_backward.argtypes = [c_void_p, ctypes.POINTER(c_void_p), c_void_p]
+    L.ffn_train_forward.argtypes = [c_void_p] + [c_void_p] * 9 + [c_int32, c_uint64, c_int64, c_int64, c_int32] + \
+        [c_void_p] * 9 + [c_void_p]
+    L.ffn_composite_backward.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
+                                         c_void_p]
+    L.ffn_train_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
+    L._train_bound = True
+
+
+def _p(t: Optional[torch.Tensor]) -> c_void_p:
+    return c_void_p(0 if t is None else t.data_ptr())
+
+
+def _mm_f32(a_t: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """(K,M)^T-free helper: returns a_t.T @ b in float32 from 16-bit inputs (fp32 accumulation)."""
+    a = a_t.t()
+    if b.dtype != a.dtype:
+        b = b.to(a.dtype)
+    try:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    except TypeError:
+        return torch.mm(a.float(), b.float())
+
+
+def enc_permutation(num_freq: int, include_inputs: bool, device) -> torch.Tensor:
+    """index of OUR encoding-chunk column for every reference column of [cos(3F) | sin(3F) | x(3)]."""
+    idx = []
+    for sn in (0, 1):
+        for k in range(num_freq):
+            for j in range(3):
+                idx.append(6 * k + 2 * j + sn)
+    if include_inputs:
+        idx += [60, 61, 62]
+    return torch.tensor(idx, dtype=torch.long, device=device)
+
+
+class RenderNeRF(torch.autograd.Function):
+    """(color, alpha, depth) = render(model, rays); gradients flow to the model parameters only."""
+
+    @staticmethod
+    def forward(ctx, model, spec, include_depth, *params):
+        L = _lib.lib()
+        _bind(L)
+        device = params[0].device
+        eng = _engine.get_engine(model, device)
+        net = eng.net
+        ns, nm, nd = c_int32(), c_int32(), c_int32()
+        _lib._check(L.ffn_train_slots(net.handle, ctypes.byref(ns), ctypes.byref(nm), ctypes.byref(nd)),
+                    "ffn_train_slots")
+        R, S = spec["R"], spec["S"]
+        M = R * S
+        f32 = dict(dtype=torch.float32, device=device)
+        color = torch.empty((R, 3), **f32)
+        alpha = torch.empty((R,), **f32)
+        depth = torch.empty((R,), **f32) if include_depth else None
+        raw = torch.empty((M, 4), **f32)
+        save_h = torch.empty((ns.value, M, 256), dtype=torch.bfloat16, device=device)
+        save_mask = torch.empty((nm.value, M, 8), dtype=torch.int32, device=device)
+        save_enc = torch.empty((2, M, 64), dtype=torch.float16, device=device)
+        if spec["mode"] == "rays":
+            t_vals = torch.empty((R, S), **f32)
+            a = spec
+            args = [None, None, None, a["starts"], a["directions"], a["near"], a["far"], a["lin"], a["jitter"]]
+            strat, seed = int(a["stratified"]), a["seed"]
+        else:
+            t_vals = spec["t_values"]
+            args = [spec["positions"], spec["view_directions"], spec["t_values"], None, None, None, None, None, None]
+            strat, seed = 0, 0
+        keep = [t for t in args if t is not None]
+        with torch.cuda.device(device):
+            _lib._check(L.ffn_train_forward(
+                net.handle, *[_p(t) for t in args], strat, c_uint64(seed & (2 ** 64 - 1)), 0, R, S,
+                _p(color), _p(alpha), _p(depth), _p(raw), _p(t_vals if spec["mode"] == "rays" else None),
+                _p(save_h), _p(save_mask), _p(save_enc), _p(net._nan_flag), _lib._stream()), "ffn_train_forward")
+        ctx.model, ctx.net, ctx.R, ctx.S, ctx.n_dz = model, net, R, S, nd.value
+        ctx.save_for_backward(raw, t_vals, save_h, save_mask, save_enc, *params)
+        ctx.keep = keep
+        ctx.mark_non_differentiable(*([depth] if depth is not None else []))
+        if depth is None:
+            return color, alpha
+        return color, alpha, depth
+
+    @staticmethod
+    def backward(ctx, g_color, g_alpha, *_):
+        L = _lib.lib()
+        raw, t_vals, save_h, save_mask, save_enc, *params = ctx.saved_tensors
+        model, net, R, S = ctx.model, ctx.net, ctx.R, ctx.S
+        M = R * S
+        device = raw.device
+        gc = (g_color if g_color is not None else torch.zeros((R, 3), device=device)).contiguous().float()
+        ga = g_alpha.contiguous().float() if g_alpha is not None else None
+        d_raw = torch.empty((M, 4), dtype=torch.float32, device=device)
+        dz = torch.empty((ctx.n_dz, M, 256), dtype=torch.bfloat16, device=device)
+        lins = _engine._linear_list(model)
+        wptr = (c_void_p * len(lins))(*[l.weight.data_ptr() for l in lins])
+        with torch.cuda.device(device):
+            _lib._check(L.ffn_composite_backward(_p(raw), _p(t_vals), R, S, _p(gc), _p(ga), _p(d_raw),
+                                                 _lib._stream()), "ffn_composite_backward")
+            _lib._check(L.ffn_net_pack_backward(net.handle, wptr, _lib._stream()), "ffn_net_pack_backward")
+            _lib._check(L.ffn_train_backward(net.handle, _p(d_raw), _p(save_mask), M, _p(dz), _lib._stream()),
+                        "ffn_train_backward")
+
+        p = model.params
+        nL = p["num_layers"]
+        skips = set(p["skips"])
+        perm_p = enc_permutation(p["num_freq_pos"], p["include_inputs"], device)
+        perm_v = enc_permutation(p["num_freq_view"], p["include_inputs"], device)
+        enc_p = save_enc[0].to(torch.bfloat16)
+        enc_v = save_enc[1].to(torch.bfloat16)
+        grads: List[Optional[torch.Tensor]] = []
+
+        def bias_grad(d):
+            return d.sum(0, dtype=torch.float32)
+
+        # trunk layers (nerf_model.py:111-116)
+        for i in range(nL):
+            dzi = dz[i]
+            if i == 0:
+                gw = _mm_f32(dzi, enc_p)[:, perm_p]
+            else:
+                gw = _mm_f32(dzi, save_h[i - 1])
+                if i in skips:
+                    gw = torch.cat([gw, _mm_f32(dzi, enc_p)[:, perm_p]], dim=1)
+            grads += [gw, bias_grad(dzi)]
+        # opacity_out (nerf_model.py:118): sigma_raw = w_op . h_L + b
+        dsig = d_raw[:, 3:4]
+        h_last = save_h[nL - 1]
+        grads += [(dsig.t() @ h_last.float()), dsig.sum(0)]
+        # bottleneck (nerf_model.py:119)
+        d_b = dz[nL]
+        grads += [_mm_f32(d_b, h_last), bias_grad(d_b)]
+        # hidden_view (nerf_model.py:121-122): input [bottleneck | enc_view]
+        dz_v = dz[nL + 1][:, :128]
+        gw = torch.cat([_mm_f32(dz_v, save_h[nL]), _mm_f32(dz_v, enc_v)[:, perm_v]], dim=1)
+        grads += [gw, bias_grad(dz_v)]
+        # color_out (nerf_model.py:123)
+        d_rgb = d_raw[:, :3]
+        h_v = save_h[nL + 1][:, :128]
+        grads += [d_rgb.t() @ h_v.float(), d_rgb.sum(0)]
+
+        out = []
+        for g, prm in zip(grads, params):
+            out.append(g.reshape(prm.shape).to(prm.dtype) if prm.requires_grad else None)
+        return (None, None, None, *out)
+
+
+def render_nerf_train(model, ray_samples, include_depth: bool, lin_fn):
+    """Entry used by ``Raycaster.render`` under autograd for NeRF models on CUDA."""
+    from .ray_sampler import RayBundle
+    lins = _engine._linear_list(model)
+    params = []
+    for l in lins:
+        params += [l.weight, l.bias]
+    if isinstance(ray_samples, RayBundle):
+        b = ray_samples
+        R, S = b.num_rays, b.num_samples
+        spec = {"mode": "rays", "R": R, "S": S, "starts": _lib._f32c(b.starts, "starts"),
+                "directions": _lib._f32c(b.directions, "directions"), "near": _lib._f32c(b.near, "near"),
+                "far": _lib._f32c(b.far, "far"), "lin": lin_fn(S),
+                "jitter": None if b.jitter is None else _lib._f32c(b.jitter, "jitter"),
+                "stratified": b.stratified, "seed": b.seed}
+    else:
+        R, S = ray_samples.positions.shape[:2]
+        spec = {"mode": "samples", "R": R, "S": S,
+                "positions": _lib._f32c(ray_samples.positions, "positions"),
+                "view_directions": _lib._f32c(ray_samples.view_directions, "view_directions"),
+                "t_values": _lib._f32c(ray_samples.t_values, "t_values")}
+    if S > 256:
+        raise _lib.FFNError("training render supports at most 256 samples per ray")
+    res = RenderNeRF.apply(model, spec, bool(include_depth), *params)
+    if include_depth:
+        return res
+    return res[0], res[1], None

@@ -49,6 +49,17 @@ struct PackHead {           // a small output head evaluated on CUDA cores in fp
   int linear, in_features, first_out, n_out;
 };
 
+// transposed-weight packing recipe of the backward (dgrad) program, see ffn_train.cuh
+struct BwdPackArgs {
+  const float* w[FFN_MAX_LAYERS + 4];
+  int n_layers;
+  struct Layer {
+    int n_chunks;
+    uint32_t w_offset;
+    int lin[kMaxChunksPerLayer], inf[kMaxChunksPerLayer], koff[kMaxChunksPerLayer], kcnt[kMaxChunksPerLayer];
+  } L[kMaxMmaLayers];
+};
+
 struct ffn_net {
   int kind = 0;             // ENC_*
   int bf16 = 0;
@@ -71,7 +82,17 @@ struct ffn_net {
   size_t scratch_bytes = 0;
   long long gen = 0;            // bumped by every pack
   bool packed = false;
+  // training (NeRF handles): backward program + slot bookkeeping
+  bool trainable = false;
+  LayerDesc layers_bwd[kMaxMmaLayers];
+  int num_layers_bwd = 0;
+  BwdPackArgs bwd_pack;
+  uint8_t* d_wpack_bwd = nullptr;
+  size_t wpack_bwd_bytes = 0;
+  int n_save = 0, n_mask = 0, n_dz = 0;
+  int bwd_first_cols = 0, bwd_first_heads = 0, bwd_first_mask = 0, bwd_first_save = 0, bwd_sigma_chunk = 0;
 };
+static int build_nerf_backward(ffn_net* net, int L);
 
 static std::atomic<long long> g_gen{1};
 static long long g_loaded_gen = 0;   // generation currently resident in c_params
@@ -315,9 +336,9 @@ static int finalize_net(ffn_net* net) {
       return fail("libffn_b200 needs an sm_100 (B200) device, found sm_" + std::to_string(prop.major) +
                   std::to_string(prop.minor));
     g_num_sms = prop.multiProcessorCount;
-    CUDA_TRY(cudaFuncSetAttribute(ffn_render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(ffn_render_kernel<false, PASS_INFER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kSmemTotal));
-    CUDA_TRY(cudaFuncSetAttribute(ffn_render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(ffn_render_kernel<true, PASS_INFER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kSmemTotal));
   }
   return 0;
@@ -403,7 +424,7 @@ extern "C" int ffn_nerf_create(const ffn_nerf_desc_t* d, ffn_net_t** out) {
   net->num_layers = nl;
   net->heads.push_back(PackHead{L, 256, 3, 1});        // opacity_out -> out[3]
   net->heads.push_back(PackHead{L + 3, 128, 0, 3});    // color_out   -> out[0..2]
-  if (finalize_net(net)) { ffn_net_destroy(net); return 1; }
+  if (finalize_net(net) || build_nerf_backward(net, L)) { ffn_net_destroy(net); return 1; }
   ConstParams* h = new ConstParams();
   memset(h, 0, sizeof(ConstParams));
   for (int k = 0; k < Fp; ++k) h->freq_pos[k] = d->freq_pos[k];
@@ -516,7 +537,7 @@ extern "C" int ffn_ffmlp_create(int32_t num_hidden, int32_t num_channels, int32_
 extern "C" void ffn_net_destroy(ffn_net_t* net) {
   if (!net) return;
   cudaFree(net->d_wpack); cudaFree(net->d_colmap); cudaFree(net->d_cparams);
-  cudaFree(net->d_ffm_a); cudaFree(net->d_ffm_b); cudaFree(net->d_scratch); cudaFree(net->d_stats);
+  cudaFree(net->d_ffm_a); cudaFree(net->d_ffm_b); cudaFree(net->d_scratch); cudaFree(net->d_stats); cudaFree(net->d_wpack_bwd);
   delete net;
 }
 
@@ -559,7 +580,7 @@ extern "C" int ffn_net_pack(ffn_net_t* net, const float* const* weights, const f
 // ============================================================================================
 // launches
 // ============================================================================================
-static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream) {
+static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int pass = PASS_INFER) {
   if (!net->packed) return fail("net has no packed weights: call ffn_net_pack first");
   if (ka.M <= 0) return 0;
   if (g_loaded_gen != net->gen) {
@@ -567,9 +588,15 @@ static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream) {
                                      cudaMemcpyDeviceToDevice, stream));
     g_loaded_gen = net->gen;
   }
-  ka.wpack = net->d_wpack;
-  memcpy(ka.layers, net->layers, sizeof(net->layers));
-  ka.num_layers = net->num_layers;
+  if (pass == PASS_BWD) {
+    ka.wpack = net->d_wpack_bwd;
+    memcpy(ka.layers, net->layers_bwd, sizeof(net->layers_bwd));
+    ka.num_layers = net->num_layers_bwd;
+  } else {
+    ka.wpack = net->d_wpack;
+    memcpy(ka.layers, net->layers, sizeof(net->layers));
+    ka.num_layers = net->num_layers;
+  }
   ka.enc_kind = net->kind;
   ka.f_pos = net->f_pos; ka.f_view = net->f_view; ka.include_inputs = net->include_inputs;
   ka.use_view = net->use_view; ka.emb = net->emb; ka.ffm_a = net->d_ffm_a; ka.ffm_b = net->d_ffm_b;
@@ -582,8 +609,12 @@ static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream) {
   if (tiles > 0x7fffffffLL) return fail("too many rows for one launch");
   ka.num_tiles = (int)tiles;
   const int grid = (int)std::min<long long>(tiles, g_num_sms);
-  if (net->bf16) ffn_render_kernel<true><<<grid, kThreads, kSmemTotal, stream>>>(ka);
-  else ffn_render_kernel<false><<<grid, kThreads, kSmemTotal, stream>>>(ka);
+  if (pass == PASS_BWD) ffn_render_kernel<true, PASS_BWD><<<grid, kThreads, kSmemTotal, stream>>>(ka);
+  else if (pass == PASS_TRAIN_FWD) {
+    if (net->bf16) ffn_render_kernel<true, PASS_TRAIN_FWD><<<grid, kThreads, kSmemTotal, stream>>>(ka);
+    else ffn_render_kernel<false, PASS_TRAIN_FWD><<<grid, kThreads, kSmemTotal, stream>>>(ka);
+  } else if (net->bf16) ffn_render_kernel<true, PASS_INFER><<<grid, kThreads, kSmemTotal, stream>>>(ka);
+  else ffn_render_kernel<false, PASS_INFER><<<grid, kThreads, kSmemTotal, stream>>>(ka);
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -718,3 +749,5 @@ extern "C" int ffn_debug_stats(ffn_net_t* net, uint64_t* out8) {
   CUDA_TRY(cudaMemset(net->d_stats, 0, 8 * sizeof(unsigned long long)));
   return 0;
 }
+
+#include "ffn_train.cuh"

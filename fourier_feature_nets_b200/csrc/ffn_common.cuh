@@ -35,7 +35,12 @@ enum : uint8_t {
   EPI_LINEAR_ACT = 1,   // act = acc + b              -> next A operand
   EPI_RELU_HEAD = 2,    // h = relu(acc + b); out[0 .. head_n) = head_w . h + head_b ; no A write
   EPI_ENC_PART2 = 3,    // no accumulator read: write the second half of a wide encoding into act chunks
+  EPI_BWD_LINEAR = 4,   // backward: dz = acc                      -> next A operand (+ saved)
+  EPI_BWD_MASK = 5,     // backward: dz = acc * relu'(h[mask_idx]) -> next A operand (+ saved)
 };
+
+// kernel passes
+enum : int { PASS_INFER = 0, PASS_TRAIN_FWD = 1, PASS_BWD = 2 };
 
 struct LayerDesc {
   uint32_t w_offset;                       // byte offset of this layer's packed weights
@@ -50,6 +55,9 @@ struct LayerDesc {
   uint8_t ksteps[kMaxChunksPerLayer];      // UMMA K-steps (of 16) per K-chunk
   uint8_t head_n, has_bias, pad1, pad2;    // EPI_RELU_HEAD: outputs 0..head_n-1; has_bias: bias tile present
   uint32_t bias_off;                       // byte offset of the packed bias tile (N x 32 B, see kBiasTile*)
+  int8_t save_idx;                         // training: slot of this layer's output in save_h / dz_out (-1 none)
+  int8_t mask_idx;                         // training fwd: slot of the ReLU bitmask written; bwd: bitmask applied
+  uint8_t pad3, pad4;
 };
 
 // Bias is folded into the accumulator by one extra K=16 UMMA per layer:
@@ -116,6 +124,17 @@ struct KernelArgs {
   int32_t dbg_flags;           // bit 0: swap LBO/SBO roles of the no-swizzle descriptors (bring-up aid)
   float* dbg_out;              // (M,256)
   unsigned long long* stats;   // optional [8]: issuer-warp cycle counters (FFN_STATS=1), see ffn_debug_stats
+  // training (PASS_TRAIN_FWD writes, PASS_BWD reads masks / writes dz)
+  __nv_bfloat16* save_h;       // [n_save][M][256] layer outputs (bf16, post-activation)
+  uint32_t* save_mask;         // [n_mask][M][8]   ReLU sign words (bit 31-j of word b <-> column 32b+j is <= 0)
+  __half* save_enc;            // [2][M][64]       position / view encoding rows as fed to the UMMA (our column order)
+  const float* d_raw;          // PASS_BWD: (M,4) gradient w.r.t. the raw network outputs [rgb | sigma]
+  __nv_bfloat16* dz_out;       // PASS_BWD: [n_dz][M][256] gradients w.r.t. the pre-activations
+  int32_t bwd_first_cols;      // PASS_BWD: width of the first dz tile (128 NeRF hidden_view, 256 FourierFeatureMLP)
+  int32_t bwd_first_heads;     //           output heads feeding it (3 rgb | 4)
+  int32_t bwd_first_mask;      //           sign-mask slot of that hidden layer
+  int32_t bwd_first_save;      //           dz_out slot it is written to
+  int32_t bwd_sigma_chunk;     //           1: d(sigma_raw) goes to column 0 of the encoding chunk
   int32_t num_tiles;
 };
 

@@ -72,7 +72,7 @@ __device__ __forceinline__ float philox_uniform(unsigned long long seed, unsigne
 template <bool kBF16>
 __device__ __forceinline__ void write_enc_posenc(uint32_t row_addr, uint32_t row7, float x0,
                                                  float x1, float x2, const float* freq, int nfreq,
-                                                 bool include_inputs) {
+                                                 bool include_inputs, uint4* gsave = nullptr) {
   uint32_t pk[32];
   const float x[3] = {x0, x1, x2};
 #pragma unroll
@@ -95,6 +95,10 @@ __device__ __forceinline__ void write_enc_posenc(uint32_t row_addr, uint32_t row
   for (uint32_t u = 0; u < 8; ++u)
     ptx::st_shared_v4(row_addr + ((u ^ row7) << 4), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2],
                       pk[4 * u + 3]);
+  if (gsave) {   // training: the 64-wide row exactly as the UMMA reads it (un-swizzled, our column order)
+#pragma unroll
+    for (uint32_t u = 0; u < 8; ++u) gsave[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+  }
 }
 
 // FourierFeatureMLP encoding (fourier_feature_models.py:66-68): feature e of (pi x) @ B gives
@@ -164,10 +168,83 @@ __device__ __forceinline__ void store_act_block(const uint32_t (&v)[32], uint32_
   }
 }
 
+// training forward: bf16 copy (post-activation) of 32 columns of one row to HBM, and the sign word of
+// the accumulator block: bit (31-j) = 1 <=> column j is negative, i.e. ReLU'(.) = 0
+template <bool kRelu>
+__device__ __forceinline__ void save_block_global(const uint32_t (&v)[32], __nv_bfloat16* grow,
+                                                  uint32_t* gmask) {
+  uint4* dst = reinterpret_cast<uint4*>(grow);
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    dst[q] = make_uint4(
+        ptx::pack2<true, kRelu>(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])),
+        ptx::pack2<true, kRelu>(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
+        ptx::pack2<true, kRelu>(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
+        ptx::pack2<true, kRelu>(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
+  if (gmask) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) w = __funnelshift_l(v[j], w, 1);
+    *gmask = w;
+  }
+}
+
+// backward: zero the columns whose forward pre-activation was negative (sign word from the forward)
+__device__ __forceinline__ void apply_sign_mask(uint32_t (&v)[32], uint32_t w) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] &= ~static_cast<uint32_t>(static_cast<int>(w << j) >> 31);
+}
+
+// One whole layer epilogue on the "lean" path: accumulator (bias already inside) -> [ReLU | sign mask] ->
+// 16-bit A tile in shared memory, TMEM loads double-buffered against the conversion of the previous
+// block.  Training passes additionally stream a bf16 copy (and the ReLU sign words) to HBM.
+//   kPass = PASS_INFER      store only
+//   kPass = PASS_TRAIN_FWD  + bf16 copy to gh, sign words to gm (when kRelu)
+//   kPass = PASS_BWD        kMask: multiply by ReLU' from the sign words at gm; A tile and HBM copy in bf16
+template <bool kBF16, bool kRelu, int kPass, bool kMask>
+__device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int nblk, uint32_t act_row,
+                                                    uint32_t row7, __nv_bfloat16* gh, uint32_t* gm,
+                                                    bool valid) {
+  uint32_t va[32], vb[32];
+  uint32_t mwords[8];
+  if constexpr (kPass == PASS_BWD && kMask) {
+    const uint4 m0 = valid ? __ldg(reinterpret_cast<const uint4*>(gm)) : make_uint4(~0u, ~0u, ~0u, ~0u);
+    const uint4 m1 = valid ? __ldg(reinterpret_cast<const uint4*>(gm) + 1) : make_uint4(~0u, ~0u, ~0u, ~0u);
+    mwords[0] = m0.x; mwords[1] = m0.y; mwords[2] = m0.z; mwords[3] = m0.w;
+    mwords[4] = m1.x; mwords[5] = m1.y; mwords[6] = m1.z; mwords[7] = m1.w;
+  }
+  auto one = [&](uint32_t (&v)[32], int b) {
+    const uint32_t chunk_row = act_row + (uint32_t)(b >> 1) * kChunkBytesA;
+    const uint32_t u0 = (uint32_t)(b & 1) * 4u;
+    if constexpr (kPass == PASS_BWD) {
+      if constexpr (kMask) apply_sign_mask(v, mwords[b]);
+      store_act_block<true, false>(v, chunk_row, row7, u0);
+      if (valid && gh) save_block_global<false>(v, gh + b * 32, nullptr);
+    } else {
+      store_act_block<kBF16, kRelu>(v, chunk_row, row7, u0);
+      if constexpr (kPass == PASS_TRAIN_FWD) {
+        if (valid && gh) save_block_global<kRelu>(v, gh + b * 32, (kRelu && gm) ? gm + b : nullptr);
+      }
+    }
+  };
+  ptx::tmem_ld32(taddr_base, va);
+#pragma unroll
+  for (int b = 0; b < 8; b += 2) {
+    if (b < nblk) {
+      ptx::tmem_wait_ld(va);
+      ptx::tmem_ld32(taddr_base + (uint32_t)(b + 1) * 32u, vb);
+      one(va, b);
+      ptx::tmem_wait_ld(vb);
+      if (b + 2 < nblk) ptx::tmem_ld32(taddr_base + (uint32_t)(b + 2) * 32u, va);
+      one(vb, b + 1);
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------
 // the kernel
 // ----------------------------------------------------------------------------------------
-template <bool kBF16>
+template <bool kBF16, int kPass>
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_render_kernel(const __grid_constant__ KernelArgs args) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -330,7 +407,38 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       float px = 0.f, py = 0.f, pz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, tval = 0.f;
       long long ray = 0;
       int sidx = 0;
-      if (valid) {
+      if constexpr (kPass == PASS_BWD) {
+        // first A operand of the dgrad chain: gradient w.r.t. the last hidden layer's pre-activation,
+        //   dz[j] = relu'(h[j]) * sum_o d_raw[o] * W_head[o][j]     (color_out / final Linear, fp32)
+        // and d(sigma_raw) in column 0 of the encoding chunk (multiplies opacity_out's weights)
+        const float4 g = valid ? __ldg(reinterpret_cast<const float4*>(args.d_raw) + row_g)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int nb0 = args.bwd_first_cols >> 5;
+        const uint32_t* mw = args.save_mask + ((size_t)args.bwd_first_mask * args.M + (valid ? row_g : 0)) * 8;
+        __nv_bfloat16* gdz = args.dz_out + ((size_t)args.bwd_first_save * args.M + (valid ? row_g : 0)) * 256;
+        for (int b = 0; b < nb0; ++b) {
+          uint32_t v[32];
+          const int c0 = b * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float a = g.x * c_params.head_w[0][c0 + j];
+            a = fmaf(g.y, c_params.head_w[1][c0 + j], a);
+            a = fmaf(g.z, c_params.head_w[2][c0 + j], a);
+            if (args.bwd_first_heads == 4) a = fmaf(g.w, c_params.head_w[3][c0 + j], a);
+            v[j] = __float_as_uint(a);
+          }
+          apply_sign_mask(v, valid ? __ldg(mw + b) : 0xffffffffu);
+          store_act_block<true, false>(v, slot_base + (uint32_t)(b >> 1) * kChunkBytesA + row_off, row7,
+                                       (uint32_t)(b & 1) * 4u);
+          if (valid) save_block_global<false>(v, gdz + c0, nullptr);
+        }
+        if (args.bwd_sigma_chunk) {
+#pragma unroll
+          for (uint32_t u = 0; u < 8; ++u)
+            ptx::st_shared_v4(enc_row_addr + ((u ^ row7) << 4), u == 0 ? ptx::pack2<true, false>(g.w, 0.f) : 0u,
+                              0u, 0u, 0u);
+        }
+      } else if (valid) {
         if (args.mode == MODE_RAYS) {
           ray = row_g / S;
           sidx = (int)(row_g - ray * S);
@@ -371,9 +479,14 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       }
 
       // ------------------------------------------------ first-layer A operand
-      if (args.enc_kind == ENC_NERF) {
+      if constexpr (kPass == PASS_BWD) {
+      } else if (args.enc_kind == ENC_NERF) {
+        uint4* gs = nullptr;
+        if constexpr (kPass == PASS_TRAIN_FWD) {
+          if (valid && args.save_enc) gs = reinterpret_cast<uint4*>(args.save_enc + (size_t)row_g * 64);
+        }
         write_enc_posenc<kBF16>(enc_row_addr, row7, px, py, pz, c_params.freq_pos, args.f_pos,
-                                args.include_inputs != 0);
+                                args.include_inputs != 0, gs);
       } else if (args.enc_kind == ENC_FFMLP) {
         // features [0,128) -> act chunks 0..3, [128,160) -> enc chunk
         write_enc_ffmlp<kBF16>(slot_base + row_off, row7, px, py, pz, args.ffm_b, args.ffm_a,
@@ -398,38 +511,30 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           // wide FourierFeatureMLP encodings: features [160, 256) -> act chunks 0..2
           write_enc_ffmlp<kBF16>(slot_base + row_off, row7, px, py, pz, args.ffm_b, args.ffm_a,
                                  args.emb, 160, 3);
-        } else if (ld.epi != EPI_RELU_HEAD && !ld.sigma_head && args.dbg_layer != l) {
-          // lean path (the bias is already in the accumulator): TMEM -> (ReLU) -> 16-bit pairs ->
-          // swizzled A tile; TMEM loads double-buffered against the conversion of the previous block
-          const int nblk = ld.n >> 5;
-          const uint32_t act_row = slot_base + row_off;
-          uint32_t va[32], vb[32];
-          ptx::tmem_ld32(taddr_base, va);
-          if (ld.epi == EPI_RELU_ACT) {
-#pragma unroll
-            for (int b = 0; b < 8; b += 2) {
-              if (b < nblk) {
-                ptx::tmem_wait_ld(va);
-                ptx::tmem_ld32(taddr_base + (uint32_t)(b + 1) * 32u, vb);
-                store_act_block<kBF16, true>(va, act_row + (b >> 1) * kChunkBytesA, row7, 0u);
-                ptx::tmem_wait_ld(vb);
-                if (b + 2 < nblk) ptx::tmem_ld32(taddr_base + (uint32_t)(b + 2) * 32u, va);
-                store_act_block<kBF16, true>(vb, act_row + (b >> 1) * kChunkBytesA, row7, 4u);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int b = 0; b < 8; b += 2) {
-              if (b < nblk) {
-                ptx::tmem_wait_ld(va);
-                ptx::tmem_ld32(taddr_base + (uint32_t)(b + 1) * 32u, vb);
-                store_act_block<kBF16, false>(va, act_row + (b >> 1) * kChunkBytesA, row7, 0u);
-                ptx::tmem_wait_ld(vb);
-                if (b + 2 < nblk) ptx::tmem_ld32(taddr_base + (uint32_t)(b + 2) * 32u, va);
-                store_act_block<kBF16, false>(vb, act_row + (b >> 1) * kChunkBytesA, row7, 4u);
-              }
-            }
+        } else if (ld.epi == EPI_BWD_LINEAR || ld.epi == EPI_BWD_MASK) {
+          if constexpr (kPass == PASS_BWD) {
+            const size_t rg = valid ? (size_t)row_g : 0;
+            __nv_bfloat16* gh = ld.save_idx >= 0 ? args.dz_out + ((size_t)ld.save_idx * args.M + rg) * 256 : nullptr;
+            uint32_t* gm = ld.mask_idx >= 0 ? args.save_mask + ((size_t)ld.mask_idx * args.M + rg) * 8 : nullptr;
+            if (ld.epi == EPI_BWD_MASK)
+              lean_layer_epilogue<true, false, PASS_BWD, true>(taddr_base, ld.n >> 5, slot_base + row_off, row7, gh, gm, valid);
+            else
+              lean_layer_epilogue<true, false, PASS_BWD, false>(taddr_base, ld.n >> 5, slot_base + row_off, row7, gh, gm, valid);
           }
+        } else if (ld.epi != EPI_RELU_HEAD && !ld.sigma_head && args.dbg_layer != l) {
+          // lean path (the bias is already in the accumulator)
+          const size_t rg = valid ? (size_t)row_g : 0;
+          __nv_bfloat16* gh = nullptr;
+          uint32_t* gm = nullptr;
+          if constexpr (kPass == PASS_TRAIN_FWD) {
+            if (ld.save_idx >= 0) gh = args.save_h + ((size_t)ld.save_idx * args.M + rg) * 256;
+            if (ld.mask_idx >= 0) gm = args.save_mask + ((size_t)ld.mask_idx * args.M + rg) * 8;
+          }
+          constexpr int kP = kPass == PASS_TRAIN_FWD ? PASS_TRAIN_FWD : PASS_INFER;
+          if (ld.epi == EPI_RELU_ACT)
+            lean_layer_epilogue<kBF16, true, kP, false>(taddr_base, ld.n >> 5, slot_base + row_off, row7, gh, gm, valid);
+          else
+            lean_layer_epilogue<kBF16, false, kP, false>(taddr_base, ld.n >> 5, slot_base + row_off, row7, gh, gm, valid);
         } else {
           // general path: fp32 values are needed (sigma / rgb heads on CUDA cores, debug dump)
           const int nblk = ld.n >> 5;
@@ -465,6 +570,21 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) args.dbg_out[row_g * 256 + c0 + j] = x[j];
             }
+            if constexpr (kPass == PASS_TRAIN_FWD) {
+              if (valid && ld.save_idx >= 0) {
+                uint32_t* gm = (relu && ld.mask_idx >= 0)
+                                   ? args.save_mask + ((size_t)ld.mask_idx * args.M + row_g) * 8 + b : nullptr;
+                // v still holds the raw accumulator (sign source); x holds the activated fp32 values
+                save_block_global<false>(reinterpret_cast<uint32_t(&)[32]>(x),
+                                         args.save_h + ((size_t)ld.save_idx * args.M + row_g) * 256 + c0, nullptr);
+                if (gm) {
+                  uint32_t w = 0;
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) w = __funnelshift_l(v[j], w, 1);
+                  *gm = w;
+                }
+              }
+            }
             if (to_act) {
               const uint32_t chunk_addr = slot_base + (uint32_t)(c0 >> 6) * kChunkBytesA + row_off;
               const uint32_t u0 = (uint32_t)(c0 & 63) >> 3;
@@ -485,8 +605,12 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
         }
 
         if (ld.write_view_enc) {
+          uint4* gs = nullptr;
+          if constexpr (kPass == PASS_TRAIN_FWD) {
+            if (valid && args.save_enc) gs = reinterpret_cast<uint4*>(args.save_enc + ((size_t)args.M + row_g) * 64);
+          }
           write_enc_posenc<kBF16>(enc_row_addr, row7, dx, dy, dz, c_params.freq_view, args.f_view,
-                                  args.include_inputs != 0);
+                                  args.include_inputs != 0, gs);
         }
         if (l < L - 1) {
           ptx::fence_proxy_async();
@@ -498,11 +622,10 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       ptx::tc_fence_before();
 
       // ------------------------------------------------ outputs
-      if (!args.fused) {
-        if (valid && args.raw)
-          reinterpret_cast<float4*>(args.raw)[row_g] = make_float4(out[0], out[1], out[2], out[3]);
-        continue;
-      }
+      if constexpr (kPass == PASS_BWD) continue;
+      if (valid && args.raw && (!args.fused || kPass == PASS_TRAIN_FWD))
+        reinterpret_cast<float4*>(args.raw)[row_g] = make_float4(out[0], out[1], out[2], out[3]);
+      if (!args.fused) continue;
 
       // ray_caster.py:67-93 + utils.py:72-97, one thread per sample, S | 128
       const float cr = sigmoid_f(out[0]), cg = sigmoid_f(out[1]), cb = sigmoid_f(out[2]);

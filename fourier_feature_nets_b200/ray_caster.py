@@ -31,6 +31,7 @@ class Raycaster(nn.Module):
         super().__init__()
         self.model = model
         self.check_nan_every_call = False   # True: reference behaviour (a host sync per render)
+        self.train_kernels = True           # False: differentiate the plain PyTorch definition instead
         self._lin_cache = {}
 
     # ---- the hot path -----------------------------------------------------------------
@@ -43,7 +44,14 @@ class Raycaster(nn.Module):
     def render(self, ray_samples: RaySamples, include_depth=False) -> RenderResult:
         """Render the ray samples -> per-ray colour (R,3), alpha (R), depth (R)."""
         device = next(self.model.parameters()).device
-        fused = device.type == "cuda" and _engine.supported(self.model) and not _needs_grad(self.model)
+        needs_grad = _needs_grad(self.model)
+        fused = device.type == "cuda" and _engine.supported(self.model) and not needs_grad
+        if (device.type == "cuda" and needs_grad and getattr(self.model, "_ffn_kind", None) == "nerf"
+                and self.train_kernels):
+            from .autograd import render_nerf_train
+            color, alpha, depth = render_nerf_train(self.model, ray_samples, include_depth,
+                                                    lambda S: self._lin(S, device))
+            return RenderResult(color, alpha, depth)
         if not fused:
             if device.type == "cuda" and not _engine.supported(self.model):
                 raise _lib.FFNError("no libffn_b200 engine for %s" % type(self.model).__name__)

@@ -117,6 +117,35 @@ int ffn_composite(const float* raw, const float* t_values, int64_t num_rays, int
 int ffn_blend_weights(const float* t_values, const float* opacity, int64_t num_rays,
                       int32_t num_samples, float* weights, void* stream);
 
+/* ---- training step (ray_caster.py:95-101,319-329): forward with saves, compositing backward, dgrad chain.
+ * Weight gradients dW = dz^T x are plain GEMMs over the saved tensors and are left to the caller. ---- */
+
+/* slot counts of the workspaces: save_h [n_save][M][256] bf16, save_mask [n_mask][M][8] u32,
+ * dz_out [n_dz][M][256] bf16 (slot = forward MMA layer index: trunk 0..L-1, bottleneck L, hidden_view L+1) */
+int ffn_train_slots(const ffn_net_t* net, int32_t* n_save, int32_t* n_mask, int32_t* n_dz);
+
+/* transposed bf16 weight images for the dgrad chain (call after the weights changed, before backward) */
+int ffn_net_pack_backward(ffn_net_t* net, const float* const* weights, void* stream);
+
+/* Raycaster.render in training mode: inputs either materialised samples (positions, view_directions,
+ * t_values; the ray pointers NULL) or rays (starts, directions, near, far, lin[, jitter]; sample pointers
+ * NULL).  Also writes raw (M,4), t_out (R,S) [rays mode], save_h, save_mask, save_enc ([2][M][64] fp16). */
+int ffn_train_forward(ffn_net_t* net, const float* positions, const float* view_directions,
+                      const float* t_values, const float* starts, const float* directions,
+                      const float* near, const float* far, const float* lin, const float* jitter,
+                      int32_t stratified, uint64_t seed, int64_t ray_offset, int64_t num_rays,
+                      int32_t num_samples, float* color, float* alpha, float* depth, float* raw,
+                      float* t_out, void* save_h, void* save_mask, void* save_enc, int32_t* nan_flag,
+                      void* stream);
+
+/* d(loss)/d(color (R,3), alpha (R) or NULL) -> d(loss)/d(raw (R,S,4))   (num_samples <= 256) */
+int ffn_composite_backward(const float* raw, const float* t_values, int64_t num_rays, int32_t num_samples,
+                           const float* grad_color, const float* grad_alpha, float* d_raw, void* stream);
+
+/* dgrad chain: d_raw (M,4) + sign words -> dz_out */
+int ffn_train_backward(ffn_net_t* net, const float* d_raw, const void* save_mask, int64_t num_points,
+                       void* dz_out, void* stream);
+
 /* Debug: dump the float32 post-activation output of MMA layer `layer` (row-major (N,256))
  * for the first `n` points.  Used by the bring-up tests only. */
 int ffn_debug_layer(ffn_net_t* net, const float* positions, const float* views, int64_t n,

@@ -1,0 +1,152 @@
+"""GPU tests of the training path (``-m gpu``): gradients from the CUDA kernels vs. fp32 autograd over the
+plain PyTorch definition of the same render (which equals the reference's, tests/test_host_logic.py).
+
+Tolerances (bf16 gradient operands, fp32 accumulation): per parameter cosine similarity >= 0.999 and
+relative L2 error <= 3e-2; compositing backward alone (fp32 end to end): <= 2e-5 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+import fourier_feature_nets_b200 as ffn
+from fourier_feature_nets_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def make_batch(R, S, seed=0, stratified=True):
+    g = torch.Generator().manual_seed(seed)
+    o = torch.tensor([0.1, 0.2, -4.0]).repeat(R, 1)
+    d = torch.nn.functional.normalize(torch.randn((R, 3), generator=g) * 0.12 + torch.tensor([0, 0, 1.0]), dim=-1)
+    near = 2.8 + 0.5 * torch.rand(R, generator=g)
+    far = near + 1.5 + torch.rand(R, generator=g)
+    u = torch.rand((R, S), generator=g) if stratified else None
+    return ffn.RayBundle(o, d, near, far, torch.arange(R), S, stratified, u)
+
+
+def trained_like_model(seed=0):
+    torch.manual_seed(seed)
+    m = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if p.requires_grad and name.endswith("weight"):
+                p.mul_(1.6)
+        m.opacity_out.weight.mul_(8.0)
+        m.color_out.weight.mul_(3.0)
+    return m.to(DEV)
+
+
+def loss_fn(out, gt_c, gt_a):
+    return (out.color - gt_c).square().mean() + 0.1 * (out.alpha - gt_a).square().mean()
+
+
+@pytest.mark.parametrize("S", [64, 128, 48])
+def test_composite_backward_matches_autograd(S):
+    from fourier_feature_nets_b200.autograd import _bind, _p
+    from fourier_feature_nets_b200.utils import blend_weights_torch
+    L = _lib.lib()
+    _bind(L)
+    R = 96
+    g = torch.Generator(device=DEV).manual_seed(S)
+    raw = torch.randn((R, S, 4), device=DEV, generator=g) * 2
+    raw[..., 3] += torch.randn((R, S), device=DEV, generator=g) * 3
+    raw.requires_grad_(True)
+    t = torch.sort(torch.rand((R, S), device=DEV, generator=g) * 2 + 3, -1)[0]
+    color = torch.sigmoid(raw[..., :3])
+    sigma = torch.nn.functional.softplus(raw[..., 3])
+    w = blend_weights_torch(t, sigma)
+    out_c = (w.unsqueeze(-1) * color).sum(-2)
+    out_a = w[:, :-1].sum(-1)
+    gc = torch.randn((R, 3), device=DEV, generator=g)
+    ga = torch.randn((R,), device=DEV, generator=g)
+    ((out_c * gc).sum() + (out_a * ga).sum()).backward()
+    d_raw = torch.empty((R, S, 4), device=DEV)
+    _lib._check(L.ffn_composite_backward(_p(raw.detach().contiguous()), _p(t), R, S, _p(gc), _p(ga), _p(d_raw),
+                                         _lib._stream()), "ffn_composite_backward")
+    ref = raw.grad
+    err = (d_raw - ref).abs().max().item()
+    assert err <= 2e-5 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("S,R", [(64, 256), (128, 96), (48, 100)])
+def test_render_gradients_match_fp32_autograd(S, R):
+    model = trained_like_model()
+    bundle = make_batch(R, S).to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    gt_c = torch.rand((R, 3), device=DEV, generator=g)
+    gt_a = torch.rand((R,), device=DEV, generator=g)
+    rc = ffn.Raycaster(model)
+
+    rc.train_kernels = False
+    model.zero_grad()
+    out_ref = rc.render(bundle, True)
+    loss_ref = loss_fn(out_ref, gt_c, gt_a)
+    loss_ref.backward()
+    ref = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    rc.train_kernels = True
+    model.zero_grad()
+    before = _lib.launch_count()
+    out = rc.render(bundle, True)
+    loss = loss_fn(out, gt_c, gt_a)
+    loss.backward()
+    assert _lib.launch_count() - before >= 4          # train fwd, composite bwd, pack^T, dgrad
+    assert abs(loss.item() - loss_ref.item()) <= 2e-3 * max(1.0, abs(loss_ref.item()))
+    assert (out.color - out_ref.color).abs().max().item() <= 2.5e-3
+    assert not out.depth.requires_grad
+    report = {}
+    for n, p in model.named_parameters():
+        if n not in ref:
+            continue
+        a, b = p.grad.flatten().double(), ref[n].flatten().double()
+        cos = (a @ b / (a.norm() * b.norm() + 1e-30)).item()
+        rel = ((a - b).norm() / (b.norm() + 1e-30)).item()
+        report[n] = (round(cos, 6), round(rel, 5))
+    print(report)
+    for n, (cos, rel) in report.items():
+        assert cos >= 0.999 and rel <= 3e-2, (n, cos, rel, report)
+    rc.check_nan()
+
+
+def test_training_steps_track_fp32_reference():
+    """A few Adam steps with clipping exactly as Raycaster.fit (ray_caster.py:319-329): the loss curve of
+    the kernel path follows the fp32 PyTorch path."""
+    losses = {}
+    for use_kernels in (False, True):
+        model = trained_like_model(3)
+        rc = ffn.Raycaster(model)
+        rc.train_kernels = use_kernels
+        opt = torch.optim.Adam(model.parameters(), 5e-4)
+        g = torch.Generator(device=DEV).manual_seed(2)
+        gt_c = torch.rand((512, 3), device=DEV, generator=g)
+        gt_a = torch.rand((512,), device=DEV, generator=g)
+        cur = []
+        for step in range(12):
+            bundle = make_batch(512, 64, seed=step).to(DEV)
+            opt.zero_grad()
+            loss = loss_fn(rc.render(bundle, True), gt_c, gt_a)
+            loss.backward()
+            torch.nn.utils.clip_grad_value_(model.parameters(), 0.1)
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)
+            opt.step()
+            cur.append(loss.item())
+        losses[use_kernels] = cur
+    a, b = np.array(losses[True]), np.array(losses[False])
+    assert b[-1] < b[0]                                   # it trains
+    assert np.abs(a - b).max() <= 0.02 * b.max(), (a, b)
+
+
+def test_inference_after_training_step_uses_new_weights():
+    model = trained_like_model(5)
+    rc = ffn.Raycaster(model)
+    bundle = make_batch(64, 64, stratified=False).to(DEV)
+    with torch.no_grad():
+        before = rc.render(bundle, False).color.clone()
+    opt = torch.optim.SGD(model.parameters(), 1e-2)
+    loss = rc.render(bundle, False).color.square().mean()
+    loss.backward()
+    opt.step()
+    with torch.no_grad():
+        after = rc.render(bundle, False).color
+    assert (after - before).abs().max().item() > 1e-5
