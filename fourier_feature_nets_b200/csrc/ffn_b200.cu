@@ -12,6 +12,7 @@
 #include "../../include/ffn_b200.h"
 #include "ffn_common.cuh"
 #include "ffn_render_kernel.cuh"
+#include "ffn_render_ts_kernel.cuh"
 
 using namespace ffn;
 
@@ -91,8 +92,18 @@ struct ffn_net {
   size_t wpack_bwd_bytes = 0;
   int n_save = 0, n_mask = 0, n_dz = 0;
   int bwd_first_cols = 0, bwd_first_heads = 0, bwd_first_mask = 0, bwd_first_save = 0, bwd_sigma_chunk = 0;
+  // v3 ("TS") inference kernel: N-half-major weight images
+  bool ts_ready = false;
+  TsLayer layers_ts[kMaxMmaLayers];
+  uint8_t* d_wpack_ts = nullptr;
+  size_t wpack_ts_bytes = 0;
+  uint32_t ts_off[kMaxMmaLayers], ts_half_bytes[kMaxMmaLayers], ts_bias_half[kMaxMmaLayers];
 };
 static int build_nerf_backward(ffn_net* net, int L);
+static int build_ts_program(ffn_net* net);
+struct PackArgs;
+static int pack_ts(ffn_net* net, const PackArgs& pa, cudaStream_t stream);
+static int launch_ts(ffn_net* net, const KernelArgs& ka, cudaStream_t stream);
 
 static std::atomic<long long> g_gen{1};
 static long long g_loaded_gen = 0;   // generation currently resident in c_params
@@ -424,7 +435,7 @@ extern "C" int ffn_nerf_create(const ffn_nerf_desc_t* d, ffn_net_t** out) {
   net->num_layers = nl;
   net->heads.push_back(PackHead{L, 256, 3, 1});        // opacity_out -> out[3]
   net->heads.push_back(PackHead{L + 3, 128, 0, 3});    // color_out   -> out[0..2]
-  if (finalize_net(net) || build_nerf_backward(net, L)) { ffn_net_destroy(net); return 1; }
+  if (finalize_net(net) || build_nerf_backward(net, L) || build_ts_program(net)) { ffn_net_destroy(net); return 1; }
   ConstParams* h = new ConstParams();
   memset(h, 0, sizeof(ConstParams));
   for (int k = 0; k < Fp; ++k) h->freq_pos[k] = d->freq_pos[k];
@@ -537,7 +548,7 @@ extern "C" int ffn_ffmlp_create(int32_t num_hidden, int32_t num_channels, int32_
 extern "C" void ffn_net_destroy(ffn_net_t* net) {
   if (!net) return;
   cudaFree(net->d_wpack); cudaFree(net->d_colmap); cudaFree(net->d_cparams);
-  cudaFree(net->d_ffm_a); cudaFree(net->d_ffm_b); cudaFree(net->d_scratch); cudaFree(net->d_stats); cudaFree(net->d_wpack_bwd);
+  cudaFree(net->d_ffm_a); cudaFree(net->d_ffm_b); cudaFree(net->d_scratch); cudaFree(net->d_stats); cudaFree(net->d_wpack_bwd); cudaFree(net->d_wpack_ts);
   delete net;
 }
 
@@ -572,6 +583,7 @@ extern "C" int ffn_net_pack(ffn_net_t* net, const float* const* weights, const f
   else pack_const_kernel<false><<<1, 256, 0, stream>>>(pa, net->d_cparams, net->d_wpack);
   g_launches += 2;
   CUDA_TRY(cudaGetLastError());
+  if (pack_ts(net, pa, stream)) return 1;
   net->gen = g_gen.fetch_add(1);
   net->packed = true;
   return 0;
@@ -608,6 +620,8 @@ static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int 
   const long long tiles = (ka.M + kTileM - 1) / kTileM;
   if (tiles > 0x7fffffffLL) return fail("too many rows for one launch");
   ka.num_tiles = (int)tiles;
+  static const bool force_v2 = getenv("FFN_FORCE_V2") != nullptr;
+  if (pass == PASS_INFER && net->ts_ready && ka.dbg_layer < 0 && !force_v2) return launch_ts(net, ka, stream);
   const int grid = (int)std::min<long long>(tiles, g_num_sms);
   if (pass == PASS_BWD) ffn_render_kernel<true, PASS_BWD><<<grid, kThreads, kSmemTotal, stream>>>(ka);
   else if (pass == PASS_TRAIN_FWD) {
@@ -751,3 +765,4 @@ extern "C" int ffn_debug_stats(ffn_net_t* net, uint64_t* out8) {
 }
 
 #include "ffn_train.cuh"
+#include "ffn_ts_host.cuh"

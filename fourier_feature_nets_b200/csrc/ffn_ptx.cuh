@@ -88,6 +88,83 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- warp-converged issue helpers -------------------------------------------------------------------
+// Called by ALL 32 lanes of a converged warp with identical operands; one lane (elect.sync) issues.  One
+// call covers a whole K-chunk (1..4 K-steps of 16): descriptors advance by 32 bytes (>>4 = 2) per step
+// inside the asm block, so the per-UMMA overhead is two adds instead of a compiler-generated
+// R2UR / vote / elect / branch "waterfall" around every single instruction.
+__device__ __forceinline__ void umma_chunk_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate, int ksteps) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pa, pt, p1, p2, p3;\n\t"
+      ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "setp.eq.u32 pt, 0, 0;\n\t"
+      "setp.gt.s32 p1, %5, 1;\n\t"
+      "setp.gt.s32 p2, %5, 2;\n\t"
+      "setp.gt.s32 p3, %5, 3;\n\t"
+      "and.pred p1, p1, pe;\n\t"
+      "and.pred p2, p2, pe;\n\t"
+      "and.pred p3, p3, pe;\n\t"
+      "add.u64 a1, %1, 2;  add.u64 b1, %2, 2;\n\t"
+      "add.u64 a2, %1, 4;  add.u64 b2, %2, 4;\n\t"
+      "add.u64 a3, %1, 6;  add.u64 b3, %2, 6;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t"
+      "@p1 tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, pt;\n\t"
+      "@p2 tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, pt;\n\t"
+      "@p3 tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(ksteps)
+      : "memory");
+}
+// A operand in TMEM: 16 K-elements = 8 columns per step
+__device__ __forceinline__ void umma_chunk_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate, int ksteps) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pa, pt, p1, p2, p3;\n\t"
+      ".reg .b32 a1, a2, a3;\n\t"
+      ".reg .b64 b1, b2, b3;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "setp.eq.u32 pt, 0, 0;\n\t"
+      "setp.gt.s32 p1, %5, 1;\n\t"
+      "setp.gt.s32 p2, %5, 2;\n\t"
+      "setp.gt.s32 p3, %5, 3;\n\t"
+      "and.pred p1, p1, pe;\n\t"
+      "and.pred p2, p2, pe;\n\t"
+      "and.pred p3, p3, pe;\n\t"
+      "add.u32 a1, %1, 8;   add.u64 b1, %2, 2;\n\t"
+      "add.u32 a2, %1, 16;  add.u64 b2, %2, 4;\n\t"
+      "add.u32 a3, %1, 24;  add.u64 b3, %2, 6;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, pa;\n\t"
+      "@p1 tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %3, pt;\n\t"
+      "@p2 tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], b2, %3, pt;\n\t"
+      "@p3 tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], b3, %3, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(ksteps)
+      : "memory");
+}
+// commit from a converged warp (one elected lane): up to two barriers in one block
+__device__ __forceinline__ void umma_commit_warp(uint32_t bar0, uint32_t bar1, uint32_t bar2) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, p1, p2;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.u32 p1, %1, 0;\n\t"
+      "setp.ne.u32 p2, %2, 0;\n\t"
+      "and.pred p1, p1, pe;\n\t"
+      "and.pred p2, p2, pe;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "@p1 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t"
+      "@p2 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%2];\n\t"
+      "}"
+      ::"r"(bar0), "r"(bar1), "r"(bar2)
+      : "memory");
+}
+
 // all previously issued tcgen05.mma of this thread -> arrive(1) on an mbarrier when complete
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)

@@ -349,25 +349,19 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
             ptx::mbar_wait(bar_w_full + 8 * stage, phase);
             if (prof) t_wait_w += clock64() - t0;
             ptx::tc_fence_after();
-            if (lane == 0) {
+            {
+              // whole (converged) warp, one elected lane issues: see ptx::umma_chunk_ss
               const uint32_t b_addr = smem_base + kSmemW + stage * kWStageBytes;
               if (c < 0) {
                 // D = ones(128x16) . bias_tile(Nx16)^T : every row of the accumulator starts at the bias
-                const uint64_t a_desc = ptx::make_kmajor_nosw_desc(smem_base + kSmemOnes, 128u, 0u);
-                const uint64_t b_desc = ptx::make_kmajor_nosw_desc(b_addr, kBiasTileLBO, kBiasTileSBO);
-                ptx::umma_f16(d_tmem, a_desc, b_desc, idesc, accumulate);
-                accumulate = 1u;
+                ptx::umma_chunk_ss(d_tmem, ptx::make_kmajor_nosw_desc(smem_base + kSmemOnes, 128u, 0u),
+                                   ptx::make_kmajor_nosw_desc(b_addr, kBiasTileLBO, kBiasTileSBO), idesc, accumulate, 1);
               } else {
-                const uint32_t a_addr = slot_base + (uint32_t)ld.src[c] * kChunkBytesA;
-                const int ks_n = ld.ksteps[c];
-                for (int ks = 0; ks < ks_n; ++ks) {
-                  ptx::umma_f16(d_tmem, ptx::make_kmajor_sw128_desc(a_addr + ks * 32),
-                                ptx::make_kmajor_sw128_desc(b_addr + ks * 32), idesc, accumulate);
-                  accumulate = 1u;
-                }
+                ptx::umma_chunk_ss(d_tmem, ptx::make_kmajor_sw128_desc(slot_base + (uint32_t)ld.src[c] * kChunkBytesA),
+                                   ptx::make_kmajor_sw128_desc(b_addr), idesc, accumulate, ld.ksteps[c]);
               }
-              ptx::umma_commit(bar_w_empty + 8 * stage);   // frees the weight stage when the MMAs retire
-              if (c == ld.n_chunks - 1) ptx::umma_commit(bar_acc_full + 8 * s);
+              accumulate = 1u;
+              ptx::umma_commit_warp(bar_w_empty + 8 * stage, c == ld.n_chunks - 1 ? bar_acc_full + 8 * s : 0u, 0u);
             }
             __syncwarp();
             if (++stage == kWStages) { stage = 0; phase ^= 1u; }
