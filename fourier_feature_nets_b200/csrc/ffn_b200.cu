@@ -617,18 +617,28 @@ static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int 
   ka.dbg_flags = env_dbg_flags;
   static const bool env_stats = getenv("FFN_STATS") != nullptr;
   ka.stats = env_stats ? net->d_stats : nullptr;
+  static const int env_lockstep = getenv("FFN_LOCKSTEP") ? atoi(getenv("FFN_LOCKSTEP")) : 0;
+  ka.lockstep = env_lockstep;
   const long long tiles = (ka.M + kTileM - 1) / kTileM;
   if (tiles > 0x7fffffffLL) return fail("too many rows for one launch");
   ka.num_tiles = (int)tiles;
-  static const bool force_v2 = getenv("FFN_FORCE_V2") != nullptr;
-  if (pass == PASS_INFER && net->ts_ready && ka.dbg_layer < 0 && !force_v2) return launch_ts(net, ka, stream);
-  const int grid = (int)std::min<long long>(tiles, g_num_sms);
-  if (pass == PASS_BWD) ffn_render_kernel<true, PASS_BWD><<<grid, kThreads, kSmemTotal, stream>>>(ka);
+  static const bool use_ts = getenv("FFN_USE_TS") != nullptr;   // experimental A-in-TMEM kernel
+  if (pass == PASS_INFER && net->ts_ready && ka.dbg_layer < 0 && use_ts) return launch_ts(net, ka, stream);
+  // clusters of 2 CTAs (TMA multicast of the weight stream): even grid, at most one CTA per SM
+  int grid = (int)std::min<long long>((tiles + 1) & ~1LL, g_num_sms & ~1);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemTotal; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (pass == PASS_BWD) CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<true, PASS_BWD>, ka));
   else if (pass == PASS_TRAIN_FWD) {
-    if (net->bf16) ffn_render_kernel<true, PASS_TRAIN_FWD><<<grid, kThreads, kSmemTotal, stream>>>(ka);
-    else ffn_render_kernel<false, PASS_TRAIN_FWD><<<grid, kThreads, kSmemTotal, stream>>>(ka);
-  } else if (net->bf16) ffn_render_kernel<true, PASS_INFER><<<grid, kThreads, kSmemTotal, stream>>>(ka);
-  else ffn_render_kernel<false, PASS_INFER><<<grid, kThreads, kSmemTotal, stream>>>(ka);
+    if (net->bf16) CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<true, PASS_TRAIN_FWD>, ka));
+    else CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<false, PASS_TRAIN_FWD>, ka));
+  } else if (net->bf16) CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<true, PASS_INFER>, ka));
+  else CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<false, PASS_INFER>, ka));
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return 0;

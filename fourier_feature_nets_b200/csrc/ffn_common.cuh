@@ -27,7 +27,12 @@ constexpr int kSmemTotal = kSmemMisc + kSmemMiscBytes;          // 232448 = 227 
 
 constexpr int kMaxMmaLayers = 12;
 constexpr int kMaxChunksPerLayer = 6;
-constexpr int kThreads = 384;                  // warp 0 producer, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 / 8-11 epilogue
+// warps 0-3: weight producer / UMMA issuer / TMEM alloc / ones tile; 4-7, 8-11: epilogue warpgroup of slot 0 / 1.
+// kHelperWG adds warps 12-15 / 16-19 that convert the upper half of the accumulator columns of slot 0 / 1.
+// Measured on B200 (profiles/r01_perf_experiments.md): it does NOT help -- draining the accumulator is bound by
+// the ~64 B/clk TMEM read port, not by per-warp latency -- so it is compiled out.
+constexpr bool kHelperWG = false;
+constexpr int kThreads = kHelperWG ? 640 : 384;
 
 // epilogue kinds
 enum : uint8_t {
@@ -136,6 +141,7 @@ struct KernelArgs {
   int32_t bwd_first_save;      //           dz_out slot it is written to
   int32_t bwd_sigma_chunk;     //           1: d(sigma_raw) goes to column 0 of the encoding chunk
   int32_t num_tiles;
+  int32_t lockstep;            // 1: both slots run the same layer and share each weight stage (see kernel)
 };
 
 }  // namespace ffn

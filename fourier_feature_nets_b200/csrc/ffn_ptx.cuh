@@ -64,6 +64,24 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
       : "memory");
 }
 
+// bulk copy multicast to the CTAs of `mask` in the cluster: same smem offset and same mbarrier offset in
+// every destination CTA
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar,
+                                            uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
@@ -162,6 +180,23 @@ __device__ __forceinline__ void umma_commit_warp(uint32_t bar0, uint32_t bar1, u
       "@p2 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%2];\n\t"
       "}"
       ::"r"(bar0), "r"(bar1), "r"(bar2)
+      : "memory");
+}
+
+// like umma_commit_warp, but bar_mc is signalled in BOTH CTAs of a 2-CTA cluster (same offset)
+__device__ __forceinline__ void umma_commit_warp_mc(uint32_t bar_mc, uint32_t bar1) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, p1;\n\t"
+      ".reg .b16 m;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.u32 p1, %1, 0;\n\t"
+      "and.pred p1, p1, pe;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t"
+      "@p1 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t"
+      "}"
+      ::"r"(bar_mc), "r"(bar1)
       : "memory");
 }
 

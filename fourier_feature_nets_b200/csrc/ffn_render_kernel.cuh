@@ -202,9 +202,10 @@ __device__ __forceinline__ void apply_sign_mask(uint32_t (&v)[32], uint32_t w) {
 //   kPass = PASS_TRAIN_FWD  + bf16 copy to gh, sign words to gm (when kRelu)
 //   kPass = PASS_BWD        kMask: multiply by ReLU' from the sign words at gm; A tile and HBM copy in bf16
 template <bool kBF16, bool kRelu, int kPass, bool kMask>
-__device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int nblk, uint32_t act_row,
+__device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int b0, int nblk, uint32_t act_row,
                                                     uint32_t row7, __nv_bfloat16* gh, uint32_t* gm,
                                                     bool valid) {
+  // this warpgroup converts the 32-column blocks [b0, b0 + nblk) of the layer (nblk = 4 or 2)
   uint32_t va[32], vb[32];
   uint32_t mwords[8];
   if constexpr (kPass == PASS_BWD && kMask) {
@@ -227,15 +228,16 @@ __device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int nbl
       }
     }
   };
-  ptx::tmem_ld32(taddr_base, va);
+  ptx::tmem_ld32(taddr_base + (uint32_t)b0 * 32u, va);
 #pragma unroll
-  for (int b = 0; b < 8; b += 2) {
-    if (b < nblk) {
+  for (int i = 0; i < 4; i += 2) {
+    if (i < nblk) {
+      const int b = b0 + i;
       ptx::tmem_wait_ld(va);
       ptx::tmem_ld32(taddr_base + (uint32_t)(b + 1) * 32u, vb);
       one(va, b);
       ptx::tmem_wait_ld(vb);
-      if (b + 2 < nblk) ptx::tmem_ld32(taddr_base + (uint32_t)(b + 2) * 32u, va);
+      if (i + 2 < nblk) ptx::tmem_ld32(taddr_base + (uint32_t)(b + 2) * 32u, va);
       one(vb, b + 1);
     }
   }
@@ -269,8 +271,8 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(bar_w_full + 8 * i, 1);
-      ptx::mbar_init(bar_w_empty + 8 * i, 1);
-      ptx::mbar_init(bar_a_ready + 8 * i, 4);   // one arrive per epilogue warp
+      ptx::mbar_init(bar_w_empty + 8 * i, 2);   // released by the UMMA issuers of BOTH CTAs of the cluster
+      ptx::mbar_init(bar_a_ready + 8 * i, kHelperWG ? 8 : 4);   // one arrive per epilogue warp
       ptx::mbar_init(bar_acc_full + 8 * i, 1);
     }
     ptx::fence_mbar_init();
@@ -290,12 +292,17 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // 2-CTA cluster: each CTA fetches half of every weight chunk and multicasts it to both (halves the L2
+  // traffic of the weight stream).  Nothing may reach the peer before its barriers are initialised.
+  const uint32_t cta_rank = ptx::cluster_ctarank();
+  ptx::cluster_sync_all();
 
   // static round-robin tile schedule: local tile k of this CTA is global tile blockIdx.x + k*grid,
   // processed in slot k & 1
   const int num_tiles = args.num_tiles;
-  const int my_tiles =
-      (int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  // every CTA runs the same number of iterations (the two CTAs of a cluster stream weights in lock step);
+  // a tile index >= num_tiles simply has no valid row
+  const int my_tiles = (num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   const int L = args.num_layers;
 
   if (warp == 0) {
@@ -306,7 +313,8 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       for (int l = 0; l < L; ++l) {
         const LayerDesc& ld = args.layers[l];
         const uint32_t bytes = (uint32_t)ld.n * 128u;
-        for (int s = 0; s < nslots; ++s) {
+        const int npass = args.lockstep ? 1 : nslots;    // lock-step: one weight stream feeds both slots
+        for (int s = 0; s < npass; ++s) {
           // chunk -1 = the layer's bias tile (N x 32 B), then the weight K-chunks
           for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
             ptx::mbar_wait(bar_w_empty + 8 * stage, phase ^ 1u);
@@ -314,9 +322,10 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
               const uint32_t nbytes = c < 0 ? (uint32_t)ld.n * 32u : bytes;
               const uint8_t* src = c < 0 ? args.wpack + ld.bias_off
                                          : args.wpack + ld.w_offset + (size_t)c * bytes;
+              const uint32_t hb = nbytes >> 1;      // my half, multicast to both CTAs
               ptx::mbar_arrive_expect_tx(bar_w_full + 8 * stage, nbytes);
-              ptx::bulk_g2s(smem_base + kSmemW + stage * kWStageBytes, src, nbytes,
-                            bar_w_full + 8 * stage);
+              ptx::bulk_g2s_mc(smem_base + kSmemW + stage * kWStageBytes + cta_rank * hb, src + cta_rank * hb, hb,
+                               bar_w_full + 8 * stage, (uint16_t)3);
             }
             __syncwarp();
             if (++stage == kWStages) { stage = 0; phase ^= 1u; }
@@ -335,6 +344,42 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       for (int l = 0; l < L; ++l) {
         const LayerDesc& ld = args.layers[l];
         const uint32_t idesc = ptx::make_idesc_f16(ld.n, kBF16);
+        if (args.lockstep) {
+          // ---- lock-step schedule: both slots run layer l together and share every weight stage
+          long long t0 = prof ? clock64() : 0;
+          for (int s = 0; s < nslots; ++s) {
+            ptx::mbar_wait(bar_a_ready + 8 * s, a_phase[s]);
+            a_phase[s] ^= 1u;
+          }
+          if (prof) t_wait_a += clock64() - t0;
+          ptx::tc_fence_after();
+          uint32_t accumulate = ld.accumulate;
+          for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
+            t0 = prof ? clock64() : 0;
+            ptx::mbar_wait(bar_w_full + 8 * stage, phase);
+            if (prof) t_wait_w += clock64() - t0;
+            ptx::tc_fence_after();
+            const uint32_t b_addr = smem_base + kSmemW + stage * kWStageBytes;
+            const bool last_chunk = c == ld.n_chunks - 1;
+            for (int s = 0; s < nslots; ++s) {
+              const uint32_t d_tmem = tmem_base + (uint32_t)s * 256u;
+              const uint32_t slot_base = smem_base + kSmemSlot0 + s * kSlotBytes;
+              if (c < 0)
+                ptx::umma_chunk_ss(d_tmem, ptx::make_kmajor_nosw_desc(smem_base + kSmemOnes, 128u, 0u),
+                                   ptx::make_kmajor_nosw_desc(b_addr, kBiasTileLBO, kBiasTileSBO), idesc, accumulate, 1);
+              else
+                ptx::umma_chunk_ss(d_tmem, ptx::make_kmajor_sw128_desc(slot_base + (uint32_t)ld.src[c] * kChunkBytesA),
+                                   ptx::make_kmajor_sw128_desc(b_addr), idesc, accumulate, ld.ksteps[c]);
+              // slot 0's accumulator is complete one chunk-time before slot 1's: release its epilogue first
+              if (s < nslots - 1 && last_chunk) ptx::umma_commit_warp(bar_acc_full + 8 * s, 0u, 0u);
+            }
+            accumulate = 1u;
+            ptx::umma_commit_warp_mc(bar_w_empty + 8 * stage, last_chunk ? bar_acc_full + 8 * (nslots - 1) : 0u);
+            __syncwarp();
+            if (++stage == kWStages) { stage = 0; phase ^= 1u; }
+          }
+          continue;
+        }
         for (int s = 0; s < nslots; ++s) {
           long long t0 = prof ? clock64() : 0;
           ptx::mbar_wait(bar_a_ready + 8 * s, a_phase[s]);
@@ -361,7 +406,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
                                    ptx::make_kmajor_sw128_desc(b_addr), idesc, accumulate, ld.ksteps[c]);
               }
               accumulate = 1u;
-              ptx::umma_commit_warp(bar_w_empty + 8 * stage, c == ld.n_chunks - 1 ? bar_acc_full + 8 * s : 0u, 0u);
+              ptx::umma_commit_warp_mc(bar_w_empty + 8 * stage, c == ld.n_chunks - 1 ? bar_acc_full + 8 * s : 0u);
             }
             __syncwarp();
             if (++stage == kWStages) { stage = 0; phase ^= 1u; }
@@ -377,7 +422,8 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
     }
   } else if (warp >= 4) {
     // ================================================================ epilogue warpgroups
-    const int slot = (warp - 4) >> 2;
+    const int slot = ((warp - 4) >> 2) & 1;
+    const int grp = warp >= 12 ? 1 : 0;            // 0: primary warpgroup of the slot, 1: helper (upper columns only)
     const int wq = warp & 3;                       // TMEM lane quadrant of this warp
     const int row = wq * 32 + lane;                // row inside the tile == TMEM lane
     const uint32_t row7 = (uint32_t)row & 7u;
@@ -391,17 +437,23 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
     float* sc_part = sc_t + 128;                   // [4][8] per-warp partials
     uint32_t acc_phase = 0;
     const int S = args.S;
+    const bool eprof = args.stats != nullptr && warp == 4 && lane == 0;
+    float* sc_sig = sc_part + 32;                  // [128] helper's partial sigma head
+    long long e_wait = 0, e_work = 0, e_front = 0, e_back = 0, e_t = 0;
 
     for (int k = slot; k < my_tiles; k += 2) {
       const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
       const long long row_g = tile * kTileM + row;
       const bool valid = row_g < args.M;
+      const long long e_t0 = eprof ? clock64() : 0;
 
       // ------------------------------------------------ inputs for this row (sample)
       float px = 0.f, py = 0.f, pz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, tval = 0.f;
       long long ray = 0;
       int sidx = 0;
-      if constexpr (kPass == PASS_BWD) {
+      if (grp != 0) {
+        // helper warpgroup: no inputs, no encoding, no compositing -- it only converts accumulator columns
+      } else if constexpr (kPass == PASS_BWD) {
         // first A operand of the dgrad chain: gradient w.r.t. the last hidden layer's pre-activation,
         //   dz[j] = relu'(h[j]) * sum_o d_raw[o] * W_head[o][j]     (color_out / final Linear, fp32)
         // and d(sigma_raw) in column 0 of the encoding chunk (multiplies opacity_out's weights)
@@ -473,7 +525,8 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       }
 
       // ------------------------------------------------ first-layer A operand
-      if constexpr (kPass == PASS_BWD) {
+      if (grp != 0) {
+      } else if constexpr (kPass == PASS_BWD) {
       } else if (args.enc_kind == ENC_NERF) {
         uint4* gs = nullptr;
         if constexpr (kPass == PASS_TRAIN_FWD) {
@@ -495,15 +548,20 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
 
       float out[4] = {0.f, 0.f, 0.f, 0.f};  // raw rgb | sigma of this sample
 
+      if (eprof) { const long long n = clock64(); e_front += n - e_t0; e_t = n; }
       for (int l = 0; l < L; ++l) {
         const LayerDesc& ld = args.layers[l];
         ptx::mbar_wait(my_acc_full, acc_phase);
         acc_phase ^= 1u;
         ptx::tc_fence_after();
+        if (eprof) { const long long n = clock64(); e_wait += n - e_t; e_t = n; }
 
+        const int nblk_all = ld.n >> 5;                 // 32-column blocks of this layer (8 or 4)
+        const int nblk_grp = kHelperWG ? nblk_all >> 1 : nblk_all;   // ... converted by this warpgroup
+        const int blk0 = grp * nblk_grp;
         if (ld.epi == EPI_ENC_PART2) {
           // wide FourierFeatureMLP encodings: features [160, 256) -> act chunks 0..2
-          write_enc_ffmlp<kBF16>(slot_base + row_off, row7, px, py, pz, args.ffm_b, args.ffm_a,
+          if (grp == 0) write_enc_ffmlp<kBF16>(slot_base + row_off, row7, px, py, pz, args.ffm_b, args.ffm_a,
                                  args.emb, 160, 3);
         } else if (ld.epi == EPI_BWD_LINEAR || ld.epi == EPI_BWD_MASK) {
           if constexpr (kPass == PASS_BWD) {
@@ -511,9 +569,9 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
             __nv_bfloat16* gh = ld.save_idx >= 0 ? args.dz_out + ((size_t)ld.save_idx * args.M + rg) * 256 : nullptr;
             uint32_t* gm = ld.mask_idx >= 0 ? args.save_mask + ((size_t)ld.mask_idx * args.M + rg) * 8 : nullptr;
             if (ld.epi == EPI_BWD_MASK)
-              lean_layer_epilogue<true, false, PASS_BWD, true>(taddr_base, ld.n >> 5, slot_base + row_off, row7, gh, gm, valid);
+              lean_layer_epilogue<true, false, PASS_BWD, true>(taddr_base, blk0, nblk_grp, slot_base + row_off, row7, gh, gm, valid);
             else
-              lean_layer_epilogue<true, false, PASS_BWD, false>(taddr_base, ld.n >> 5, slot_base + row_off, row7, gh, gm, valid);
+              lean_layer_epilogue<true, false, PASS_BWD, false>(taddr_base, blk0, nblk_grp, slot_base + row_off, row7, gh, gm, valid);
           }
         } else if (ld.epi != EPI_RELU_HEAD && !ld.sigma_head && args.dbg_layer != l) {
           // lean path (the bias is already in the accumulator)
@@ -526,17 +584,20 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           }
           constexpr int kP = kPass == PASS_TRAIN_FWD ? PASS_TRAIN_FWD : PASS_INFER;
           if (ld.epi == EPI_RELU_ACT)
-            lean_layer_epilogue<kBF16, true, kP, false>(taddr_base, ld.n >> 5, slot_base + row_off, row7, gh, gm, valid);
+            lean_layer_epilogue<kBF16, true, kP, false>(taddr_base, blk0, nblk_grp, slot_base + row_off, row7, gh, gm, valid);
           else
-            lean_layer_epilogue<kBF16, false, kP, false>(taddr_base, ld.n >> 5, slot_base + row_off, row7, gh, gm, valid);
+            lean_layer_epilogue<kBF16, false, kP, false>(taddr_base, blk0, nblk_grp, slot_base + row_off, row7, gh, gm, valid);
         } else {
           // general path: fp32 values are needed (sigma / rgb heads on CUDA cores, debug dump)
-          const int nblk = ld.n >> 5;
           const bool relu = ld.epi != EPI_LINEAR_ACT;
           const bool to_act = ld.epi != EPI_RELU_HEAD;
           float hacc[4] = {0.f, 0.f, 0.f, 0.f};
           const int hn = ld.epi == EPI_RELU_HEAD ? ld.head_n : 0;   // heads 0..hn-1 (rgb | rgb+sigma)
-          for (int b = 0; b < nblk; ++b) {
+          // output-head layers are converted by the primary warpgroup alone (their fp32 dot products stay in
+          // one thread); everything else is split between primary and helper
+          const int gb0 = hn > 0 ? 0 : blk0;
+          const int gb1 = hn > 0 ? (grp == 0 ? nblk_all : 0) : blk0 + nblk_grp;
+          for (int b = gb0; b < gb1; ++b) {
             uint32_t v[32];
             ptx::tmem_ld32(taddr_base + (uint32_t)b * 32u, v);
             ptx::tmem_wait_ld(v);
@@ -592,13 +653,13 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
               }
             }
           }
-          if (ld.sigma_head) out[3] = hacc[3] + c_params.head_b[3];
+          if (ld.sigma_head) out[3] = hacc[3];      // partial over this warpgroup's columns, combined below
 #pragma unroll
           for (int o = 0; o < 4; ++o)
             if (o < hn) out[o] = hacc[o] + c_params.head_b[o];
         }
 
-        if (ld.write_view_enc) {
+        if (ld.write_view_enc && grp == 0) {
           uint4* gs = nullptr;
           if constexpr (kPass == PASS_TRAIN_FWD) {
             if (valid && args.save_enc) gs = reinterpret_cast<uint4*>(args.save_enc + ((size_t)args.M + row_g) * 64);
@@ -612,8 +673,20 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(my_a_ready);
         }
+        if (ld.sigma_head) {
+          // sigma_raw = w_op . h + b: add the helper's partial dot product (after the UMMA issuer was released)
+          if constexpr (kHelperWG) {
+            if (grp != 0) sc_sig[row] = out[3];
+            ptx::named_bar_sync(3 + slot, 256);
+            if (grp == 0) out[3] += sc_sig[row];
+          }
+          if (grp == 0) out[3] += c_params.head_b[3];
+        }
+        if (eprof) { const long long n = clock64(); e_work += n - e_t; e_t = n; }
       }
       ptx::tc_fence_before();
+      if (grp != 0) continue;
+      const long long e_t1 = eprof ? clock64() : 0;
 
       // ------------------------------------------------ outputs
       if constexpr (kPass == PASS_BWD) continue;
@@ -692,12 +765,20 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       }
       // sc_t / sc_part are rewritten by the next tile only after its first named barrier
       ptx::named_bar_sync(bar_id, 128);
+      if (eprof) e_back += clock64() - e_t1;
+    }
+    if (eprof) {
+      atomicAdd(args.stats + 4, (unsigned long long)e_wait);
+      atomicAdd(args.stats + 5, (unsigned long long)e_work);
+      atomicAdd(args.stats + 6, (unsigned long long)e_front);
+      atomicAdd(args.stats + 7, (unsigned long long)e_back);
     }
   }
 
   // ---------------------------------------------------------------- teardown
   ptx::tc_fence_before();
   __syncthreads();
+  ptx::cluster_sync_all();     // the peer may still multicast into / commit onto this CTA's shared memory
   if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
 }
 

@@ -1,37 +1,39 @@
 // v3 inference kernel ("TS"): the hidden activations never touch shared memory.
 //
-//   * the A operand of every 256-wide layer lives in TMEM (tcgen05.mma, A in tensor memory); the epilogue
+//   * the A operand of every 256-wide layer lives in TMEM (tcgen05.mma with A in tensor memory); the epilogue
 //     converts the fp32 accumulator to 16-bit pairs and writes them straight back to TMEM with tcgen05.st.
 //     Shared memory only carries the weight stream and the two 64-wide encoding tiles, so the UMMA B reads
-//     and the TMA weight fills have the shared-memory port to themselves (the v2 kernel was bound by that
-//     port: A + B reads, TMA fills and epilogue stores = 24 KB per UMMA).
+//     and the TMA weight fills have the shared-memory port to themselves.
 //   * TMEM (512 columns): [0,256) fp32 accumulator, [256,384) and [384,512) two A buffers (256 K-elements
-//     each) that ping-pong between consecutive layers.
-//   * one 128-row tile per CTA at a time; inside a tile every layer is issued as two N-halves, so the
-//     epilogue of half 0 overlaps the UMMAs of half 1 and only the epilogue of half 1 is exposed.
-//   * 160 KB of shared memory become a 9-stage x 16 KB weight ring (one N-half of a 64-wide K chunk per
-//     stage) that hides the L2 latency completely.
-//   * warps: 0 weight producer (bulk-copy engine), 1 UMMA issuer, 2 TMEM alloc, 4-7 "front/back"
+//     each) that ping-pong between consecutive layers.  One 128-row tile per CTA at a time.
+//   * UMMAs are issued at full width (N = 256): an M=128 UMMA costs ~140 cycles whatever N is (measured),
+//     so N-halves do not pipeline.  The accumulator -> A conversion is the exposed part of every layer; it is
+//     split over TWO epilogue warpgroups (columns [0,N/2) and [N/2,N)).
+//   * the weight ring is 4 stages x 32 KB (same packed image as the v2 kernel).
+//   * 16 warps: 0 weight producer (bulk-copy engine), 1 UMMA issuer, 2 TMEM alloc, 4-7 "front/back"
 //     warpgroup (inputs, t values, sin/cos encoding tiles of the NEXT tile; compositing and pixel stores of
-//     the PREVIOUS tile), 8-11 epilogue warpgroup (TMEM -> TMEM conversions, fp32 heads).
+//     the PREVIOUS tile), 8-11 / 12-15 epilogue warpgroups (TMEM -> TMEM conversions, fp32 heads).
 #pragma once
 #include "ffn_common.cuh"
 #include "ffn_ptx.cuh"
 
 namespace ffn {
 
-constexpr int kTsStages = 9;
-constexpr int kTsStageBytes = 128 * 128;                        // one N-half (<=128 rows) of a K chunk
+constexpr int kTsThreads = 512;
+constexpr int kTsStages = 4;
+constexpr int kTsStageBytes = 256 * 128;                        // one K chunk (N <= 256 rows x 128 B)
 constexpr int kTsSmemW = 0;
 constexpr int kTsSmemEnc = kTsStages * kTsStageBytes;           // encP[2], encV[2]: 4 x 16 KB
-constexpr int kTsSmemMisc = kTsSmemEnc + 4 * kChunkBytesA;      // 208 KB
-constexpr int kTsSmemTotal = 232448;                            // 227 KB; misc region = 19 KB
+constexpr int kTsSmemMisc = kTsSmemEnc + 4 * kChunkBytesA;      // 192 KB
+constexpr int kTsSmemTotal = kTsSmemMisc + 16384;                // 208 KB
 // misc region layout (bytes from kTsSmemMisc)
-constexpr int kTsOffTmemPtr = 256, kTsOffTbuf = 512, kTsOffPart = 1536, kTsOffOnes = 1792, kTsOffRaw = 2048;
+constexpr int kTsOffTmemPtr = 256, kTsOffTbuf = 512, kTsOffPart = 1536, kTsOffOnes = 1792, kTsOffRaw = 2048,
+              kTsOffHead = 6144;   // [2 groups][128 rows] float4 partial heads
 constexpr uint32_t kTsColA0 = 256, kTsColA1 = 384;
 
 struct TsLayer {
-  uint32_t w_offset;        // byte offset of the layer image: [half0: bias tile?, chunks...][half1: ...]
+  uint32_t w_offset;        // byte offset of the layer's weight chunks (v2 image: N x 128 B per chunk)
+  uint32_t bias_off;        // byte offset of the bias tile (N x 32 B)
   uint16_t n;               // 256 or 128
   uint8_t n_chunks;
   uint8_t epi;              // EPI_RELU_ACT / EPI_LINEAR_ACT / EPI_RELU_HEAD
@@ -87,7 +89,7 @@ __device__ __forceinline__ void ts_store_block(const uint32_t (&v)[32], uint32_t
 }
 
 template <bool kBF16>
-__global__ void __launch_bounds__(kThreads, 1) ffn_render_ts_kernel(const __grid_constant__ TsArgs args) {
+__global__ void __launch_bounds__(kTsThreads, 1) ffn_render_ts_kernel(const __grid_constant__ TsArgs args) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = ptx::smem_u32(smem);
   const int warp = threadIdx.x >> 5;
@@ -95,12 +97,12 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_render_ts_kernel(const __grid
 
   // ---- misc region: barriers, tmem pointer, per-tile hand-off buffers, ones tile
   const uint32_t bars = smem_base + kTsSmemMisc;
-  const uint32_t bar_w_full = bars + 0;          // [9]
-  const uint32_t bar_w_empty = bars + 80;        // [9]
+  const uint32_t bar_w_full = bars + 0;          // [4]
+  const uint32_t bar_w_empty = bars + 80;        // [4]
   const uint32_t bar_enc_ready = bars + 160;     // [2]  front WG -> issuer
   const uint32_t bar_enc_free = bars + 176;      // [2]  issuer (commit) -> front WG
   const uint32_t bar_a_ready = bars + 192;       // [1]  epilogue WG -> issuer (next layer's A complete)
-  const uint32_t bar_acc_full = bars + 200;      // [2]  issuer (commit) -> epilogue WG, per N-half
+  const uint32_t bar_acc_full = bars + 200;      // [1]  issuer (commit) -> both epilogue WGs
   const uint32_t bar_acc_free = bars + 216;      // [1]  epilogue WG -> issuer (accumulator drained, per tile)
   const uint32_t bar_raw_ready = bars + 224;     // [2]  epilogue WG -> front/back WG
   const uint32_t bar_raw_free = bars + 240;      // [2]  front/back WG -> epilogue WG
@@ -108,6 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_render_ts_kernel(const __grid
   float* tbuf = reinterpret_cast<float*>(smem + kTsSmemMisc + kTsOffTbuf);        // [2][128] t values
   float* partbuf = reinterpret_cast<float*>(smem + kTsSmemMisc + kTsOffPart);     // [4][8] cross-warp partials
   float4* rawbuf = reinterpret_cast<float4*>(smem + kTsSmemMisc + kTsOffRaw);     // [2][128] raw rgb|sigma hand-off
+  float4* headbuf = reinterpret_cast<float4*>(smem + kTsSmemMisc + kTsOffHead);   // [2][128] per-group partial heads
   constexpr int kOnesOff = kTsOffOnes;
 
   if ((smem_base & 1023u) != 0u) {
@@ -119,12 +122,12 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_render_ts_kernel(const __grid
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(bar_enc_ready + 8 * i, 4);
       ptx::mbar_init(bar_enc_free + 8 * i, 1);
-      ptx::mbar_init(bar_acc_full + 8 * i, 1);
       ptx::mbar_init(bar_raw_ready + 8 * i, 4);
       ptx::mbar_init(bar_raw_free + 8 * i, 4);
     }
-    ptx::mbar_init(bar_a_ready, 4);
-    ptx::mbar_init(bar_acc_free, 4);
+    ptx::mbar_init(bar_a_ready, 8);
+    ptx::mbar_init(bar_acc_free, 8);
+    ptx::mbar_init(bar_acc_full, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 3) {
@@ -155,20 +158,17 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_render_ts_kernel(const __grid
     for (int k = 0; k < my_tiles; ++k) {
       for (int l = 0; l < L; ++l) {
         const TsLayer& ld = args.layers[l];
-        const uint32_t half_rows = ld.n >> 1;
-        const uint8_t* src = args.wpack + ld.w_offset;
-        for (int h = 0; h < 2; ++h) {
-          for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
-            const uint32_t nbytes = c < 0 ? half_rows * 32u : half_rows * 128u;
-            ptx::mbar_wait(bar_w_empty + 8 * stage, phase ^ 1u);
-            if (lane == 0) {
-              ptx::mbar_arrive_expect_tx(bar_w_full + 8 * stage, nbytes);
-              ptx::bulk_g2s(smem_base + kTsSmemW + stage * kTsStageBytes, src, nbytes, bar_w_full + 8 * stage);
-            }
-            __syncwarp();
-            src += nbytes;
-            if (++stage == kTsStages) { stage = 0; phase ^= 1u; }
+        const uint32_t bytes = (uint32_t)ld.n * 128u;
+        for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
+          const uint32_t nbytes = c < 0 ? (uint32_t)ld.n * 32u : bytes;
+          const uint8_t* src = c < 0 ? args.wpack + ld.bias_off : args.wpack + ld.w_offset + (size_t)c * bytes;
+          ptx::mbar_wait(bar_w_empty + 8 * stage, phase ^ 1u);
+          if (lane == 0) {
+            ptx::mbar_arrive_expect_tx(bar_w_full + 8 * stage, nbytes);
+            ptx::bulk_g2s(smem_base + kTsSmemW + stage * kTsStageBytes, src, nbytes, bar_w_full + 8 * stage);
           }
+          __syncwarp();
+          if (++stage == kTsStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -185,8 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_render_ts_kernel(const __grid
       if (prof) t_wait_a += clock64() - t0;
       for (int l = 0; l < L; ++l) {
         const TsLayer& ld = args.layers[l];
-        const uint32_t half_rows = ld.n >> 1;
-        const uint32_t idesc = ptx::make_idesc_f16(half_rows, kBF16);
+        const uint32_t idesc = ptx::make_idesc_f16(ld.n, kBF16);
         if (l > 0) {
           t0 = prof ? clock64() : 0;
           ptx::mbar_wait(bar_a_ready, a_phase);
@@ -195,37 +194,35 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_render_ts_kernel(const __grid
         }
         ptx::tc_fence_after();
         const uint32_t a_cols = tmem_base + ((l & 1) ? kTsColA1 : kTsColA0);   // layer l reads A[l&1]
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)h * half_rows;
-          uint32_t accumulate = 0u;
-          for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
-            t0 = prof ? clock64() : 0;
-            ptx::mbar_wait(bar_w_full + 8 * stage, phase);
-            if (prof) t_wait_w += clock64() - t0;
-            ptx::tc_fence_after();
-            {
-              // whole (converged) warp, one elected lane issues: see ptx::umma_chunk_*
-              const uint32_t b_addr = smem_base + kTsSmemW + stage * kTsStageBytes;
-              if (c < 0) {
-                ptx::umma_chunk_ss(d_tmem, ptx::make_kmajor_nosw_desc(smem_base + kTsSmemMisc + kOnesOff, 128u, 0u),
-                                   ptx::make_kmajor_nosw_desc(b_addr, kBiasTileLBO, kBiasTileSBO), idesc, accumulate, 1);
-              } else {
-                const int src = ld.src[c], ks_n = ld.ksteps[c];
-                if (src < 4)
-                  ptx::umma_chunk_ts(d_tmem, a_cols + (uint32_t)(src * 32), ptx::make_kmajor_sw128_desc(b_addr),
-                                     idesc, accumulate, ks_n);
-                else
-                  ptx::umma_chunk_ss(d_tmem, ptx::make_kmajor_sw128_desc(enc_tile(src - 4, par)),
-                                     ptx::make_kmajor_sw128_desc(b_addr), idesc, accumulate, ks_n);
-              }
-              accumulate = 1u;
-              const bool last_chunk = c == ld.n_chunks - 1;
-              ptx::umma_commit_warp(bar_w_empty + 8 * stage, last_chunk ? bar_acc_full + 8 * h : 0u,
-                                    (last_chunk && l == L - 1 && h == 1) ? bar_enc_free + 8 * par : 0u);
+        const uint32_t d_tmem = tmem_base;
+        uint32_t accumulate = 0u;
+        for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
+          t0 = prof ? clock64() : 0;
+          ptx::mbar_wait(bar_w_full + 8 * stage, phase);
+          if (prof) t_wait_w += clock64() - t0;
+          ptx::tc_fence_after();
+          {
+            // whole (converged) warp, one elected lane issues: see ptx::umma_chunk_*
+            const uint32_t b_addr = smem_base + kTsSmemW + stage * kTsStageBytes;
+            if (c < 0) {
+              ptx::umma_chunk_ss(d_tmem, ptx::make_kmajor_nosw_desc(smem_base + kTsSmemMisc + kOnesOff, 128u, 0u),
+                                 ptx::make_kmajor_nosw_desc(b_addr, kBiasTileLBO, kBiasTileSBO), idesc, accumulate, 1);
+            } else {
+              const int src = ld.src[c], ks_n = ld.ksteps[c];
+              if (src < 4)
+                ptx::umma_chunk_ts(d_tmem, a_cols + (uint32_t)(src * 32), ptx::make_kmajor_sw128_desc(b_addr), idesc,
+                                   accumulate, ks_n);
+              else
+                ptx::umma_chunk_ss(d_tmem, ptx::make_kmajor_sw128_desc(enc_tile(src - 4, par)),
+                                   ptx::make_kmajor_sw128_desc(b_addr), idesc, accumulate, ks_n);
             }
-            __syncwarp();
-            if (++stage == kTsStages) { stage = 0; phase ^= 1u; }
+            accumulate = 1u;
+            const bool last_chunk = c == ld.n_chunks - 1;
+            ptx::umma_commit_warp(bar_w_empty + 8 * stage, last_chunk ? bar_acc_full : 0u,
+                                  (last_chunk && l == L - 1) ? bar_enc_free + 8 * par : 0u);
           }
+          __syncwarp();
+          if (++stage == kTsStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -370,79 +367,74 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_render_ts_kernel(const __grid
       }
     }
   } else if (warp >= 8) {
-    // ================================================================ epilogue warpgroup
+    // ================================================================ epilogue warpgroups
+    // group 0 (warps 8-11) converts accumulator columns [0, n/2), group 1 (warps 12-15) columns [n/2, n)
+    const int grp = (warp - 8) >> 2;
     const int wq = warp & 3;
     const int row = wq * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
-    uint32_t full_phase = 0u;     // bit h = phase parity of bar_acc_full[h]
+    uint32_t full_phase = 0u;
     for (int k = 0; k < my_tiles; ++k) {
       const int par = k & 1;
-      float out[4] = {0.f, 0.f, 0.f, 0.f};
+      float hacc[4] = {0.f, 0.f, 0.f, 0.f};     // this group's partial heads (rgb | sigma) over its columns
       for (int l = 0; l < L; ++l) {
         const TsLayer& ld = args.layers[l];
-        const uint32_t half_rows = ld.n >> 1;
-        const int nblk_h = half_rows >> 5;                 // 32-column blocks per N-half (4 or 2)
+        const uint32_t half = ld.n >> 1;
+        const int nblk = half >> 5;                        // 32-column blocks per group (4 or 2)
         const uint32_t a_next = lane_base + (((l + 1) & 1) ? kTsColA1 : kTsColA0);
         const bool lean = ld.epi != EPI_RELU_HEAD && !ld.sigma_head;
-        float hacc[4] = {0.f, 0.f, 0.f, 0.f};
         const int hn = ld.epi == EPI_RELU_HEAD ? ld.head_n : 0;
-        for (int h = 0; h < 2; ++h) {
-          ptx::mbar_wait(bar_acc_full + 8 * h, (full_phase >> h) & 1u);
-          full_phase ^= 1u << h;
-          ptx::tc_fence_after();
-          const uint32_t acc = lane_base + (uint32_t)h * half_rows;
-          const uint32_t dst = a_next + (uint32_t)h * (half_rows >> 1);
-          if (lean) {
-            uint32_t va[32], vb[32];
-            ptx::tmem_ld32(acc, va);
+        ptx::mbar_wait(bar_acc_full, full_phase);
+        full_phase ^= 1u;
+        ptx::tc_fence_after();
+        const uint32_t acc = lane_base + (uint32_t)grp * half;
+        const uint32_t dst = a_next + (uint32_t)grp * (half >> 1);
+        if (lean) {
+          uint32_t va[32], vb[32];
+          ptx::tmem_ld32(acc, va);
 #pragma unroll
-            for (int b = 0; b < 4; b += 2) {
-              if (b < nblk_h) {
-                ptx::tmem_wait_ld(va);
-                ptx::tmem_ld32(acc + (uint32_t)(b + 1) * 32u, vb);
-                if (ld.epi == EPI_RELU_ACT) ts_store_block<kBF16, true>(va, dst + (uint32_t)b * 16u);
-                else ts_store_block<kBF16, false>(va, dst + (uint32_t)b * 16u);
-                ptx::tmem_wait_ld(vb);
-                if (b + 2 < nblk_h) ptx::tmem_ld32(acc + (uint32_t)(b + 2) * 32u, va);
-                if (ld.epi == EPI_RELU_ACT) ts_store_block<kBF16, true>(vb, dst + (uint32_t)(b + 1) * 16u);
-                else ts_store_block<kBF16, false>(vb, dst + (uint32_t)(b + 1) * 16u);
-              }
-            }
-          } else {
-            const bool relu = ld.epi != EPI_LINEAR_ACT;
-            const bool to_act = ld.epi != EPI_RELU_HEAD;
-            for (int b = 0; b < nblk_h; ++b) {
-              uint32_t v[32];
-              ptx::tmem_ld32(acc + (uint32_t)b * 32u, v);
-              ptx::tmem_wait_ld(v);
-              const int c0 = h * (int)half_rows + b * 32;
-              float x[32];
-#pragma unroll
-              for (int jx = 0; jx < 32; ++jx) {
-                const float t = __uint_as_float(v[jx]);
-                x[jx] = relu ? fmaxf(t, 0.f) : t;
-              }
-              if (ld.sigma_head) {
-#pragma unroll
-                for (int jx = 0; jx < 32; ++jx) hacc[3] = fmaf(x[jx], c_params.head_w[3][c0 + jx], hacc[3]);
-              }
-#pragma unroll
-              for (int o = 0; o < 4; ++o) {
-                if (o < hn) {
-                  float a = hacc[o];
-#pragma unroll
-                  for (int jx = 0; jx < 32; ++jx) a = fmaf(x[jx], c_params.head_w[o][c0 + jx], a);
-                  hacc[o] = a;
-                }
-              }
-              if (to_act) ts_store_block<kBF16, false>(reinterpret_cast<uint32_t(&)[32]>(x), dst + (uint32_t)b * 16u);
+          for (int b = 0; b < 4; b += 2) {
+            if (b < nblk) {
+              ptx::tmem_wait_ld(va);
+              ptx::tmem_ld32(acc + (uint32_t)(b + 1) * 32u, vb);
+              if (ld.epi == EPI_RELU_ACT) ts_store_block<kBF16, true>(va, dst + (uint32_t)b * 16u);
+              else ts_store_block<kBF16, false>(va, dst + (uint32_t)b * 16u);
+              ptx::tmem_wait_ld(vb);
+              if (b + 2 < nblk) ptx::tmem_ld32(acc + (uint32_t)(b + 2) * 32u, va);
+              if (ld.epi == EPI_RELU_ACT) ts_store_block<kBF16, true>(vb, dst + (uint32_t)(b + 1) * 16u);
+              else ts_store_block<kBF16, false>(vb, dst + (uint32_t)(b + 1) * 16u);
             }
           }
-        }
-        if (ld.sigma_head) out[3] = hacc[3] + c_params.head_b[3];
+        } else {
+          const bool relu = ld.epi != EPI_LINEAR_ACT;
+          const bool to_act = ld.epi != EPI_RELU_HEAD;
+          for (int b = 0; b < nblk; ++b) {
+            uint32_t v[32];
+            ptx::tmem_ld32(acc + (uint32_t)b * 32u, v);
+            ptx::tmem_wait_ld(v);
+            const int c0 = grp * (int)half + b * 32;
+            float x[32];
 #pragma unroll
-        for (int o = 0; o < 4; ++o)
-          if (o < hn) out[o] = hacc[o] + c_params.head_b[o];
+            for (int jx = 0; jx < 32; ++jx) {
+              const float t = __uint_as_float(v[jx]);
+              x[jx] = relu ? fmaxf(t, 0.f) : t;
+            }
+            if (ld.sigma_head) {
+#pragma unroll
+              for (int jx = 0; jx < 32; ++jx) hacc[3] = fmaf(x[jx], c_params.head_w[3][c0 + jx], hacc[3]);
+            }
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+              if (o < hn) {
+                float a = hacc[o];
+#pragma unroll
+                for (int jx = 0; jx < 32; ++jx) a = fmaf(x[jx], c_params.head_w[o][c0 + jx], a);
+                hacc[o] = a;
+              }
+            }
+            if (to_act) ts_store_block<kBF16, false>(reinterpret_cast<uint32_t(&)[32]>(x), dst + (uint32_t)b * 16u);
+          }
+        }
         if (l < L - 1) {
           ptx::tmem_wait_st();
           ptx::tc_fence_before();
@@ -454,11 +446,18 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_render_ts_kernel(const __grid
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_acc_free);
-      // hand the raw outputs of this row to the back warpgroup
-      ptx::mbar_wait(bar_raw_free + 8 * par, ((uint32_t)(k >> 1) & 1u) ^ 1u);
-      rawbuf[par * 128 + row] = make_float4(out[0], out[1], out[2], out[3]);
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_raw_ready + 8 * par);
+      // combine the two groups' partial heads and hand the raw outputs to the back warpgroup
+      headbuf[grp * 128 + row] = make_float4(hacc[0], hacc[1], hacc[2], hacc[3]);
+      ptx::named_bar_sync(2, 256);
+      if (grp == 0) {
+        const float4 o1 = headbuf[128 + row];
+        ptx::mbar_wait(bar_raw_free + 8 * par, ((uint32_t)(k >> 1) & 1u) ^ 1u);
+        rawbuf[par * 128 + row] = make_float4(hacc[0] + o1.x + c_params.head_b[0], hacc[1] + o1.y + c_params.head_b[1],
+                                              hacc[2] + o1.z + c_params.head_b[2], hacc[3] + o1.w + c_params.head_b[3]);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_raw_ready + 8 * par);
+      }
+      ptx::named_bar_sync(2, 256);     // headbuf is rewritten by the next tile
     }
   }
 

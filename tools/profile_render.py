@@ -42,6 +42,10 @@ ms = e0.elapsed_time(e1)
 print("last launch %.3f ms -> %.2f M rays/s" % (ms, R / ms / 1e3))
 
 if os.environ.get("FFN_STATS"):
-    tot, wa, ww, n = eng.net.debug_stats()[:4]
+    st = eng.net.debug_stats()
+    tot, wa, ww, n = st[:4]
+    if st[4] + st[5]:
+        print("epilogue warp 4 (per CTA, cycles): wait-acc %.0f  convert+store %.0f  front(enc) %.0f  back(composite) %.0f" % (
+            st[4] / n, st[5] / n, st[6] / n, st[7] / n))
     print("issuer warp: total %.0f cyc/CTA, wait-epilogue %.1f%%, wait-weights %.1f%%, issuing %.1f%%" % (
         tot / n, 100 * wa / tot, 100 * ww / tot, 100 * (tot - wa - ww) / tot))
