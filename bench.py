@@ -288,7 +288,10 @@ def main():
                        "jitter": "in-kernel Philox4x32-10"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "peak_source": peak_src + " (of measured)",
-                         "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
+                         # ncu (one --set full capture) measured dram bytes for a launch of
+                         # `rays_per_launch` rays; traffic scales linearly with the rays of a launch
+                         "traffic": None if traffic is None else
+                         traffic["dram_bytes_per_launch"] * R / traffic.get("rays_per_launch", R),
                          "kernel": "ffn_render_kernel<fp16>", "kernel_ms": kernel_ms,
                          "flop_per_launch": R * SAMPLES * FLOP_PER_SAMPLE,
                          "hbm_gbs_algorithmic": R * 52 / (kernel_ms / 1e3) / 1e9},

@@ -12,9 +12,11 @@ from .image_dataset import ImageDataset, RayDataset
 from .nerf_model import NeRF
 from .ray_caster import Raycaster
 from .ray_dataset_modes import Mode
-from .ray_sampler import RayBundle, RaySampler, RaySamples
-from .utils import (RenderResult, calculate_blend_weights, exponential_lr_decay, linspace,
+from .ray_sampler import FocusBundle, RayBundle, RaySampler, RaySamples
+from .utils import (ETABar, RenderResult, calculate_blend_weights, exponential_lr_decay, linspace,
                     load_model, orbit)
+from .visualizers import (ActivationVisualizer, ComparisonVisualizer, EvaluationVisualizer,
+                          OrbitVideoVisualizer)
 
 RayCaster = Raycaster   # BASELINE.json spells it this way; the reference class is ``Raycaster``
 
@@ -22,5 +24,6 @@ __version__ = "0.1.0"
 
 __all__ = ["CameraInfo", "Resolution", "MLP", "NeRF", "BasicFourierMLP", "FourierFeatureMLP",
            "PositionalFourierMLP", "GaussianFourierMLP", "Raycaster", "RayCaster", "RaySampler",
-           "RaySamples", "RayBundle", "RenderResult", "Mode", "ImageDataset", "RayDataset", "calculate_blend_weights",
-           "exponential_lr_decay", "linspace", "load_model", "orbit", "__version__"]
+           "RaySamples", "RayBundle", "FocusBundle", "RenderResult", "Mode", "ImageDataset", "RayDataset", "calculate_blend_weights",
+           "exponential_lr_decay", "linspace", "load_model", "orbit", "ETABar", "EvaluationVisualizer",
+           "OrbitVideoVisualizer", "ActivationVisualizer", "ComparisonVisualizer", "__version__"]

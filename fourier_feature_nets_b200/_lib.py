@@ -93,6 +93,12 @@ def lib() -> ctypes.CDLL:
     L.ffn_composite.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p]
     L.ffn_blend_weights.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
+    L.ffn_focus_t.argtypes = [c_void_p, c_int32] + [c_void_p] * 9 + [c_int32, c_uint64, c_int64, c_int64, c_int32,
+                                                                     c_void_p, c_void_p]
+    L.ffn_focus_sample.argtypes = [c_void_p] + [c_void_p] * 11 + [c_int32, c_uint64, c_int64, c_int64, c_int32,
+                                                                  c_void_p, c_void_p]
+    L.ffn_render_rays_t.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p]
     _lib = L
     return L
 
@@ -101,6 +107,7 @@ EXPORTED_SYMBOLS = [
     "ffn_version", "ffn_last_error", "ffn_nerf_create", "ffn_ffmlp_create", "ffn_net_destroy",
     "ffn_net_num_linear", "ffn_net_pack", "ffn_mlp_forward", "ffn_render_samples",
     "ffn_render_rays", "ffn_composite", "ffn_blend_weights", "ffn_debug_layer", "ffn_debug_stats", "ffn_launch_count",
+    "ffn_focus_t", "ffn_focus_sample", "ffn_render_rays_t",
     "ffn_train_slots", "ffn_net_pack_backward", "ffn_train_forward", "ffn_composite_backward",
     "ffn_train_backward",
 ]
@@ -263,6 +270,35 @@ class Net:
                    "ffn_render_rays")
         return color, alpha, depth, t_out
 
+    def focus_sample(self, starts, directions, near, far, near_u, far_u, lin_c, lin_u, jitter_u, u_focus,
+                     stratified: bool, seed: int, num_samples: int) -> torch.Tensor:
+        """coarse sigma pass of THIS net + inverse-transform sampling -> sorted t (R, num_samples)."""
+        o, d = _f32c(starts, "starts"), _f32c(directions, "directions")
+        nr, fr = _f32c(near, "near"), _f32c(far, "far")
+        nu, fu = _f32c(near_u, "near_u"), _f32c(far_u, "far_u")
+        lc, lu = _f32c(lin_c, "lin_c"), _f32c(lin_u, "lin_u")
+        ju = _f32c(jitter_u, "jitter_u") if jitter_u is not None else None
+        uf = _f32c(u_focus, "u_focus") if u_focus is not None else None
+        R = o.shape[0]
+        t = torch.empty((R, num_samples), dtype=torch.float32, device=o.device)
+        with torch.cuda.device(self.device):
+            _check(lib().ffn_focus_sample(self.handle, _ptr(o), _ptr(d), _ptr(nr), _ptr(fr), _ptr(nu), _ptr(fu),
+                                          _ptr(lc), _ptr(lu), _ptr(lc), _ptr(ju), _ptr(uf), int(bool(stratified)),
+                                          c_uint64(seed & (2**64 - 1)), 0, R, num_samples, _ptr(t), _stream()),
+                   "ffn_focus_sample")
+        return t
+
+    def render_rays_t(self, starts, directions, t_values, include_depth: bool):
+        o, d, t = _f32c(starts, "starts"), _f32c(directions, "directions"), _f32c(t_values, "t_values")
+        R, S = t.shape
+        color = torch.empty((R, 3), dtype=torch.float32, device=o.device)
+        alpha = torch.empty((R,), dtype=torch.float32, device=o.device)
+        depth = torch.empty((R,), dtype=torch.float32, device=o.device) if include_depth else None
+        with torch.cuda.device(self.device):
+            _check(lib().ffn_render_rays_t(self.handle, _ptr(o), _ptr(d), _ptr(t), R, S, _ptr(color), _ptr(alpha),
+                                           _ptr(depth), _ptr(self._nan_flag), _stream()), "ffn_render_rays_t")
+        return color, alpha, depth
+
     def debug_stats(self):
         out = (ctypes.c_uint64 * 8)()
         lib().ffn_debug_stats.argtypes = [c_void_p, c_void_p]
@@ -302,3 +338,21 @@ def blend_weights(t_values: torch.Tensor, opacity: torch.Tensor) -> torch.Tensor
     with torch.cuda.device(t.device):
         _check(lib().ffn_blend_weights(_ptr(t), _ptr(sg), R, S, _ptr(w), _stream()), "ffn_blend_weights")
     return w
+
+
+def focus_t(raw_sigma: torch.Tensor, near, far, near_u, far_u, lin_c, lin_u, jitter_u, u_focus,
+            stratified: bool, seed: int, num_samples: int) -> torch.Tensor:
+    """``ffn_focus_t`` on given coarse opacity logits (R, S_c) or raw outputs (R, S_c, 4)."""
+    raw = _f32c(raw_sigma, "raw")
+    stride = 4 if raw.dim() == 3 else 1
+    R = raw.shape[0]
+    t = torch.empty((R, num_samples), dtype=torch.float32, device=raw.device)
+    ju = _f32c(jitter_u, "jitter_u") if jitter_u is not None else None
+    uf = _f32c(u_focus, "u_focus") if u_focus is not None else None
+    with torch.cuda.device(raw.device):
+        _check(lib().ffn_focus_t(_ptr(raw), stride, _ptr(_f32c(near, "near")), _ptr(_f32c(far, "far")),
+                                 _ptr(_f32c(near_u, "near_u")), _ptr(_f32c(far_u, "far_u")), _ptr(_f32c(lin_c, "lin_c")),
+                                 _ptr(_f32c(lin_u, "lin_u")), _ptr(_f32c(lin_c, "lin_c")), _ptr(ju), _ptr(uf),
+                                 int(bool(stratified)), c_uint64(seed & (2**64 - 1)), 0, R, num_samples, _ptr(t),
+                                 _stream()), "ffn_focus_t")
+    return t

@@ -776,3 +776,4 @@ extern "C" int ffn_debug_stats(ffn_net_t* net, uint64_t* out8) {
 
 #include "ffn_train.cuh"
 #include "ffn_ts_host.cuh"
+#include "ffn_focus.cuh"

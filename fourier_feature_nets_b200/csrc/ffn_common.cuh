@@ -79,7 +79,7 @@ constexpr int kSmemOnes = kSmemMisc + 2816;   // 256-byte ones tile at the end o
 enum : int32_t { ENC_NERF = 0, ENC_FFMLP = 1, ENC_NONE = 2 };
 
 // input modes
-enum : int32_t { MODE_POINTS = 0, MODE_SAMPLES = 1, MODE_RAYS = 2 };
+enum : int32_t { MODE_POINTS = 0, MODE_SAMPLES = 1, MODE_RAYS = 2, MODE_RAYS_T = 3 };
 
 // Broadcast-read parameters: head weights (sigma / rgb / final layer) and frequency tables.  Lives in
 // __constant__ memory; re-uploaded (device-to-device, stream ordered) whenever the

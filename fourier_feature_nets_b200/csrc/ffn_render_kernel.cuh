@@ -205,7 +205,7 @@ template <bool kBF16, bool kRelu, int kPass, bool kMask>
 __device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int b0, int nblk, uint32_t act_row,
                                                     uint32_t row7, __nv_bfloat16* gh, uint32_t* gm,
                                                     bool valid) {
-  // this warpgroup converts the 32-column blocks [b0, b0 + nblk) of the layer (nblk = 4 or 2)
+  // this warpgroup converts the 32-column blocks [b0, b0 + nblk) of the layer (nblk = 8, 4 or 2)
   uint32_t va[32], vb[32];
   uint32_t mwords[8];
   if constexpr (kPass == PASS_BWD && kMask) {
@@ -230,7 +230,7 @@ __device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int b0,
   };
   ptx::tmem_ld32(taddr_base + (uint32_t)b0 * 32u, va);
 #pragma unroll
-  for (int i = 0; i < 4; i += 2) {
+  for (int i = 0; i < 8; i += 2) {
     if (i < nblk) {
       const int b = b0 + i;
       ptx::tmem_wait_ld(va);
@@ -507,6 +507,17 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           py = __fadd_rn(__ldg(args.org + ray * 3 + 1), __fmul_rn(tval, dy));
           pz = __fadd_rn(__ldg(args.org + ray * 3 + 2), __fmul_rn(tval, dz));
           if (args.t_out) args.t_out[row_g] = tval;
+        } else if (args.mode == MODE_RAYS_T) {
+          // per-ray origin / direction, explicit per-sample t (focus sampling): ray_sampler.py:393-397
+          ray = row_g / S;
+          sidx = (int)(row_g - ray * S);
+          tval = __ldg(args.tvals + row_g);
+          dx = __ldg(args.dir + ray * 3 + 0);
+          dy = __ldg(args.dir + ray * 3 + 1);
+          dz = __ldg(args.dir + ray * 3 + 2);
+          px = __fadd_rn(__ldg(args.org + ray * 3 + 0), __fmul_rn(tval, dx));
+          py = __fadd_rn(__ldg(args.org + ray * 3 + 1), __fmul_rn(tval, dy));
+          pz = __fadd_rn(__ldg(args.org + ray * 3 + 2), __fmul_rn(tval, dz));
         } else {
           px = __ldg(args.pos + row_g * 3 + 0);
           py = __ldg(args.pos + row_g * 3 + 1);

@@ -266,6 +266,14 @@ __global__ void __launch_bounds__(kTsThreads, 1) ffn_render_ts_kernel(const __gr
             py = __fadd_rn(__ldg(args.org + ray * 3 + 1), __fmul_rn(tval, dy));
             pz = __fadd_rn(__ldg(args.org + ray * 3 + 2), __fmul_rn(tval, dz));
             if (args.t_out) args.t_out[row_g] = tval;
+          } else if (args.mode == MODE_RAYS_T) {
+            // per-ray origin / direction, explicit per-sample t (focus sampling): ray_sampler.py:393-397
+            const long long ray = row_g / S;
+            tval = __ldg(args.tvals + row_g);
+            dx = __ldg(args.dir + ray * 3 + 0); dy = __ldg(args.dir + ray * 3 + 1); dz = __ldg(args.dir + ray * 3 + 2);
+            px = __fadd_rn(__ldg(args.org + ray * 3 + 0), __fmul_rn(tval, dx));
+            py = __fadd_rn(__ldg(args.org + ray * 3 + 1), __fmul_rn(tval, dy));
+            pz = __fadd_rn(__ldg(args.org + ray * 3 + 2), __fmul_rn(tval, dz));
           } else {
             px = __ldg(args.pos + row_g * 3 + 0); py = __ldg(args.pos + row_g * 3 + 1); pz = __ldg(args.pos + row_g * 3 + 2);
             dx = __ldg(args.dir + row_g * 3 + 0); dy = __ldg(args.dir + row_g * 3 + 1); dz = __ldg(args.dir + row_g * 3 + 2);

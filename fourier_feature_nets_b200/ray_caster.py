@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from . import _lib
 from . import engine as _engine
 from .nerf_model import _needs_grad
-from .ray_sampler import RayBundle, RaySampler, RaySamples
+from .ray_sampler import FocusBundle, RayBundle, RaySampler, RaySamples
 from .utils import RenderResult, blend_weights_torch, exponential_lr_decay
 
 LogEntry = NamedTuple("LogEntry", [("step", int), ("timestamp", float),
@@ -49,6 +49,9 @@ class Raycaster(nn.Module):
         if (device.type == "cuda" and needs_grad and getattr(self.model, "_ffn_kind", None) == "nerf"
                 and self.train_kernels):
             from .autograd import render_nerf_train
+            if isinstance(ray_samples, FocusBundle):     # t values come from the (frozen) coarse model
+                with torch.no_grad():
+                    ray_samples = ray_samples.materialize()
             color, alpha, depth = render_nerf_train(self.model, ray_samples, include_depth,
                                                     lambda S: self._lin(S, device))
             return RenderResult(color, alpha, depth)
@@ -58,7 +61,11 @@ class Raycaster(nn.Module):
             return self._render_torch(ray_samples, include_depth)
 
         eng = _engine.get_engine(self.model, device)
-        if isinstance(ray_samples, RayBundle):
+        if isinstance(ray_samples, FocusBundle):
+            b = ray_samples
+            t = b.focus_t()                  # coarse sigma pass + CDF + inverse transform + sort, on the GPU
+            color, alpha, depth = eng.net.render_rays_t(b.starts, b.directions, t, include_depth)
+        elif isinstance(ray_samples, RayBundle):
             b = ray_samples
             color, alpha, depth, _ = eng.net.render_rays(
                 b.starts, b.directions, b.near, b.far, self._lin(b.num_samples, device), b.jitter,
@@ -227,3 +234,13 @@ class Raycaster(nn.Module):
                     visualizer.visualize(step, render_image, render_act)
                 step += 1
         return log
+
+
+    def to_scenepic(self, dataset, *args, **kwargs):
+        """The reference writes an interactive scenepic HTML here (ray_caster.py:379-488): lecture
+        visualisation, out of scope.  Returns an object whose ``save_as_html`` writes a stub page."""
+        class _Stub:
+            def save_as_html(self, path, *a, **k):
+                with open(path, "w") as f:
+                    f.write("<html><body>scenepic visualisation is not produced by the B200 build</body></html>")
+        return _Stub()

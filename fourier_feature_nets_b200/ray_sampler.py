@@ -124,6 +124,46 @@ class RayBundle(RaySamples):
         return len(self.near)
 
 
+class FocusBundle(RayBundle):
+    """``RayBundle`` whose samples are S//2 (stratified) uniform + S - S//2 CDF-focused t values, sorted
+    (ray_sampler.py:388-392).  The coarse sigma pass, the CDF and the inverse-transform sampling run on the
+    GPU per batch (``ffn_focus_sample``) instead of once per dataset on the host."""
+
+    def __new__(cls, starts, directions, near, far, near_raw, far_raw, rays, num_samples, stratified,
+                jitter_u, u_focus, seed, coarse_model):
+        self = super().__new__(cls, starts, directions, near, far, rays, num_samples, stratified, jitter_u, seed)
+        self.near_raw, self.far_raw = near_raw, far_raw     # un-annealed segment: the CDF lives on it
+        self.u_focus = u_focus
+        self.coarse_model = coarse_model
+        return self
+
+    def focus_t(self) -> torch.Tensor:
+        """Sorted t values (R,S) on the device of the rays (must be CUDA)."""
+        from . import engine as _engine
+        S = self.num_samples
+        n_u, n_f = S // 2, S - S // 2
+        dev = self.starts.device
+        eng = _engine.get_engine(self.coarse_model, dev)
+        return eng.net.focus_sample(self.starts, self.directions, self.near_raw, self.far_raw, self.near, self.far,
+                                    torch.linspace(0, 1, n_f).to(dev), torch.linspace(0, 1, n_u).to(dev),
+                                    self.jitter, self.u_focus, self.stratified, self.seed, S)
+
+    def materialize(self) -> RaySamples:
+        if self._cache is None:
+            t = self.focus_t()
+            n, S = len(self.near), self.num_samples
+            dirs = self.directions.reshape(n, 1, 3).repeat(1, S, 1)
+            pos = self.starts.reshape(n, 1, 3) + t.unsqueeze(-1) * dirs
+            self._cache = RaySamples(pos, dirs, t, tuple.__getitem__(self, 3))
+        return self._cache
+
+    def _map(self, fn) -> "FocusBundle":
+        return FocusBundle(fn(self.starts), fn(self.directions), fn(self.near), fn(self.far), fn(self.near_raw),
+                           fn(self.far_raw), None if self.rays is None else fn(self.rays), self.num_samples,
+                           self.stratified, None if self.jitter is None else fn(self.jitter),
+                           None if self.u_focus is None else fn(self.u_focus), self.seed, self.coarse_model)
+
+
 def _determine_cdf(t_values: torch.Tensor, opacity: torch.Tensor) -> torch.Tensor:
     """Coarse weights -> CDF over the S-2 interior bins (ray_sampler.py:59-67)."""
     weights = blend_weights_torch(t_values, opacity)[:, 1:-1] + 1e-5
@@ -152,8 +192,15 @@ class RaySampler:
         self.stratified = stratified
         self.opacity_model = opacity_model
         self.focus_sampling = opacity_model is not None
+        # an opacity model the CUDA engine can evaluate is sampled lazily, per batch, on the GPU: no
+        # constructor-time sigma pass over every ray, no (num_rays, S_c-1) CDF table
+        self.lazy_focus = False
         if self.focus_sampling:
             self.opacity_model.eval()
+            from . import engine as _engine
+            params = list(self.opacity_model.parameters())
+            self.lazy_focus = bool(_engine.supported(self.opacity_model) and params and params[0].is_cuda
+                                   and getattr(self.opacity_model, "use_view", False))
         self.batch_size = batch_size
         self.seed = 20080524
         self._draws = 0
@@ -174,14 +221,14 @@ class RaySampler:
             directions.append(d)
             near_far.append(nf)
             valid.append(torch.from_numpy(ok))
-            if self.focus_sampling:
+            if self.focus_sampling and not self.lazy_focus:
                 t = linspace(nf[0], nf[1], num_focus)
                 cdfs.append(_determine_cdf(t, self._determine_opacity(t, o, d)))
         self.starts = torch.cat(starts)
         self.directions = torch.cat(directions)
         self.near_far = torch.cat(near_far, -1)
         self.valid_mask = torch.cat(valid)
-        if self.focus_sampling:
+        if self.focus_sampling and not self.lazy_focus:
             self.cdfs = torch.cat(cdfs)
         self._invalid_set = None
 
@@ -191,7 +238,7 @@ class RaySampler:
         self.directions = self.directions.to(device)
         self.near_far = self.near_far.to(device)
         self.valid_mask = self.valid_mask.to(device)
-        if self.focus_sampling:
+        if self.focus_sampling and not self.lazy_focus:
             self.cdfs = self.cdfs.to(device)
         return self
 
@@ -315,6 +362,19 @@ class RaySampler:
             self._draws += 1
             return RayBundle(starts, directions, near, far, idx_dev, self.num_samples,
                              self.stratified, jitter, self.seed + self._draws)
+
+        if self.lazy_focus:
+            near_raw, far_raw = self.near_far[:, idx_dev]
+            n_u = self.num_samples // 2
+            jitter_u = u_focus = None
+            on_device = starts.is_cuda if self.device_jitter is None else self.device_jitter
+            if self.stratified and not on_device:
+                # the reference's draw order: uniform part (:383) then focus part (:313)
+                jitter_u = torch.rand((n, n_u), dtype=torch.float32)
+                u_focus = torch.rand((n, self.num_samples - n_u), dtype=torch.float32)
+            self._draws += 1
+            return FocusBundle(starts, directions, near, far, near_raw, far_raw, idx_dev, self.num_samples,
+                               self.stratified, jitter_u, u_focus, self.seed + self._draws, self.opacity_model)
 
         num_uniform = self.num_samples // 2
         t = linspace(near, far, num_uniform)

@@ -134,3 +134,35 @@ def orbit(up_dir: np.ndarray, forward_dir: np.ndarray, num_frames: int,
         cameras.append(CameraInfo.create("cam%d" % len(cameras), resolution, intrinsics,
                                          ext.astype(np.float32)))
     return cameras
+
+
+class ETABar:
+    """Console progress bar with the interface the scripts use (``next``/``info``/``finish``); the reference
+    derives it from the ``progress`` package (utils.py:36-69)."""
+
+    def __init__(self, message: str, max: int = 100):
+        self.message, self.max, self.index, self.suffix = message, max, 0, ""
+        import time
+        self._t0 = time.time()
+
+    def next(self, n: int = 1):
+        import sys
+        import time
+        self.index += n
+        if self.index == self.max or self.index % builtin_max(1, self.max // 50) == 0:
+            el = time.time() - self._t0
+            eta = el / builtin_max(1, self.index) * (self.max - self.index)
+            sys.stdout.write("\r%s %5.1f%% - %ds %s" % (self.message, 100.0 * self.index / builtin_max(1, self.max), eta, self.suffix))
+            sys.stdout.flush()
+
+    def info(self, text: str):
+        self.suffix = text
+
+    def writeln(self, line: str):
+        print(line)
+
+    def finish(self):
+        print()
+
+
+builtin_max = max

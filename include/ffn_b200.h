@@ -117,6 +117,30 @@ int ffn_composite(const float* raw, const float* t_values, int64_t num_rays, int
 int ffn_blend_weights(const float* t_values, const float* opacity, int64_t num_rays,
                       int32_t num_samples, float* weights, void* stream);
 
+/* ---- hierarchical ("focus") sampling, ray_sampler.py:59-67,234-269,301-357,388-392, done per batch on
+ * the GPU instead of a constructor-time pass that stores a (num_rays, S_c-1) CDF table on the host ---- */
+
+/* Sorted t values (R,S) from the coarse model's raw outputs `raw` ((R, S_c, raw_stride), opacity logit in the last
+ * channel; S_c = S - S/2) at t_c = near + lin_c (far - near).  near_u/far_u: the (possibly annealed) segment of
+ * the S/2 uniform samples; lin_u = linspace(0,1,S/2), lin_c = lin_f = linspace(0,1,S_c); jitter_u (R,S/2) and
+ * u_focus (R,S_c) are the reference's torch.rand draws (NULL: Philox when stratified, else no jitter / lin_f). */
+int ffn_focus_t(const float* raw, int32_t raw_stride, const float* near, const float* far, const float* near_u,
+                const float* far_u, const float* lin_c, const float* lin_u, const float* lin_f,
+                const float* jitter_u, const float* u_focus, int32_t stratified, uint64_t seed,
+                int64_t ray_offset, int64_t num_rays, int32_t num_samples, float* t_out, void* stream);
+
+/* coarse sigma pass of `coarse` (fused MLP kernel, scratch inside the handle) + ffn_focus_t */
+int ffn_focus_sample(ffn_net_t* coarse, const float* starts, const float* directions, const float* near,
+                     const float* far, const float* near_u, const float* far_u, const float* lin_c,
+                     const float* lin_u, const float* lin_f, const float* jitter_u, const float* u_focus,
+                     int32_t stratified, uint64_t seed, int64_t ray_offset, int64_t num_rays,
+                     int32_t num_samples, float* t_out, void* stream);
+
+/* Raycaster.render on rays with explicit per-sample t (R,S): positions = starts + t * directions in-kernel */
+int ffn_render_rays_t(ffn_net_t* net, const float* starts, const float* directions, const float* t_values,
+                      int64_t num_rays, int32_t num_samples, float* color, float* alpha, float* depth,
+                      int32_t* nan_flag, void* stream);
+
 /* ---- training step (ray_caster.py:95-101,319-329): forward with saves, compositing backward, dgrad chain.
  * Weight gradients dW = dz^T x are plain GEMMs over the saved tensors and are left to the caller. ---- */
 
