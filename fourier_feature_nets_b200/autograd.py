@@ -14,6 +14,7 @@ checked in tests/test_gpu_training.py (cosine >= 0.999, relative L2 error <= 3e-
 from __future__ import annotations
 
 import ctypes
+import math
 from ctypes import c_int32, c_int64, c_uint64, c_void_p
 from typing import List, Optional
 
@@ -174,6 +175,86 @@ class RenderNeRF(torch.autograd.Function):
         return (None, None, None, *out)
 
 
+def _positions_from_spec(spec, t_vals):
+    if spec["mode"] == "rays":
+        R, S = spec["R"], spec["S"]
+        return (spec["starts"].reshape(R, 1, 3) + t_vals.reshape(R, S, 1) * spec["directions"].reshape(R, 1, 3)).reshape(-1, 3)
+    return spec["positions"].reshape(-1, 3)
+
+
+class RenderFFMLP(torch.autograd.Function):
+    """Same as :class:`RenderNeRF` for ``FourierFeatureMLP`` models (3 -> [256]*H -> 4, no view branch)."""
+
+    @staticmethod
+    def forward(ctx, model, spec, include_depth, *params):
+        L = _lib.lib()
+        _bind(L)
+        device = params[0].device
+        net = _engine.get_engine(model, device).net
+        ns, nm, nd = c_int32(), c_int32(), c_int32()
+        _lib._check(L.ffn_train_slots(net.handle, ctypes.byref(ns), ctypes.byref(nm), ctypes.byref(nd)), "ffn_train_slots")
+        R, S = spec["R"], spec["S"]
+        M = R * S
+        f32 = dict(dtype=torch.float32, device=device)
+        color, alpha = torch.empty((R, 3), **f32), torch.empty((R,), **f32)
+        depth = torch.empty((R,), **f32) if include_depth else None
+        raw = torch.empty((M, 4), **f32)
+        save_h = torch.empty((ns.value, M, 256), dtype=torch.bfloat16, device=device)
+        save_mask = torch.empty((nm.value, M, 8), dtype=torch.int32, device=device)
+        if spec["mode"] == "rays":
+            t_vals = torch.empty((R, S), **f32)
+            a = spec
+            args = [None, None, None, a["starts"], a["directions"], a["near"], a["far"], a["lin"], a["jitter"]]
+            strat, seed = int(a["stratified"]), a["seed"]
+        else:
+            t_vals = spec["t_values"]
+            args = [spec["positions"], None, spec["t_values"], None, None, None, None, None, None]
+            strat, seed = 0, 0
+        with torch.cuda.device(device):
+            _lib._check(L.ffn_train_forward(
+                net.handle, *[_p(t) for t in args], strat, c_uint64(seed & (2 ** 64 - 1)), 0, R, S,
+                _p(color), _p(alpha), _p(depth), _p(raw), _p(t_vals if spec["mode"] == "rays" else None),
+                _p(save_h), _p(save_mask), _p(None), _p(net._nan_flag), _lib._stream()), "ffn_train_forward")
+        ctx.model, ctx.net, ctx.R, ctx.S, ctx.n_dz, ctx.spec = model, net, R, S, nd.value, spec
+        ctx.save_for_backward(raw, t_vals, save_h, save_mask, *params)
+        ctx.mark_non_differentiable(*([depth] if depth is not None else []))
+        return (color, alpha) if depth is None else (color, alpha, depth)
+
+    @staticmethod
+    def backward(ctx, g_color, g_alpha, *_):
+        L = _lib.lib()
+        raw, t_vals, save_h, save_mask, *params = ctx.saved_tensors
+        model, net, R, S = ctx.model, ctx.net, ctx.R, ctx.S
+        M = R * S
+        device = raw.device
+        gc = (g_color if g_color is not None else torch.zeros((R, 3), device=device)).contiguous().float()
+        ga = g_alpha.contiguous().float() if g_alpha is not None else None
+        d_raw = torch.empty((M, 4), dtype=torch.float32, device=device)
+        dz = torch.empty((ctx.n_dz, M, 256), dtype=torch.bfloat16, device=device)
+        lins = _engine._linear_list(model)
+        wptr = (c_void_p * len(lins))(*[l.weight.data_ptr() for l in lins])
+        with torch.cuda.device(device):
+            _lib._check(L.ffn_composite_backward(_p(raw), _p(t_vals), R, S, _p(gc), _p(ga), _p(d_raw), _lib._stream()),
+                        "ffn_composite_backward")
+            _lib._check(L.ffn_net_pack_backward(net.handle, wptr, _lib._stream()), "ffn_net_pack_backward")
+            _lib._check(L.ffn_train_backward(net.handle, _p(d_raw), _p(save_mask), M, _p(dz), _lib._stream()),
+                        "ffn_train_backward")
+        H = len(lins) - 1
+        # layer 0 input: the encoding, recomputed in the reference's column order (fourier_feature_models.py:66-68)
+        pos = _positions_from_spec(ctx.spec, t_vals)
+        if model.b_values is None:
+            x0 = pos
+        else:
+            e = (math.pi * pos) @ model.b_values
+            x0 = torch.cat([model.a_values * e.cos(), model.a_values * e.sin()], dim=-1)
+        grads = [_mm_f32(dz[0], x0.to(torch.bfloat16)), dz[0].sum(0, dtype=torch.float32)]
+        for i in range(1, H):
+            grads += [_mm_f32(dz[i], save_h[i - 1]), dz[i].sum(0, dtype=torch.float32)]
+        grads += [d_raw.t() @ save_h[H - 1].float(), d_raw.sum(0)]          # final Linear 256 -> 4
+        out = [g.reshape(p.shape).to(p.dtype) if p.requires_grad else None for g, p in zip(grads, params)]
+        return (None, None, None, *out)
+
+
 def render_nerf_train(model, ray_samples, include_depth: bool, lin_fn):
     """Entry used by ``Raycaster.render`` under autograd for NeRF models on CUDA."""
     from .ray_sampler import RayBundle
@@ -193,11 +274,13 @@ def render_nerf_train(model, ray_samples, include_depth: bool, lin_fn):
         R, S = ray_samples.positions.shape[:2]
         spec = {"mode": "samples", "R": R, "S": S,
                 "positions": _lib._f32c(ray_samples.positions, "positions"),
-                "view_directions": _lib._f32c(ray_samples.view_directions, "view_directions"),
+                "view_directions": (_lib._f32c(ray_samples.view_directions, "view_directions")
+                                    if model.use_view else None),
                 "t_values": _lib._f32c(ray_samples.t_values, "t_values")}
     if S > 256:
         raise _lib.FFNError("training render supports at most 256 samples per ray")
-    res = RenderNeRF.apply(model, spec, bool(include_depth), *params)
+    fn = RenderNeRF if model._ffn_kind == "nerf" else RenderFFMLP
+    res = fn.apply(model, spec, bool(include_depth), *params)
     if include_depth:
         return res
     return res[0], res[1], None

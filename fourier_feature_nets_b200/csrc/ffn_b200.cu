@@ -100,6 +100,7 @@ struct ffn_net {
   uint32_t ts_off[kMaxMmaLayers], ts_half_bytes[kMaxMmaLayers], ts_bias_half[kMaxMmaLayers];
 };
 static int build_nerf_backward(ffn_net* net, int L);
+static int build_ffmlp_backward(ffn_net* net, int H);
 static int build_ts_program(ffn_net* net);
 struct PackArgs;
 static int pack_ts(ffn_net* net, const PackArgs& pa, cudaStream_t stream);
@@ -533,7 +534,7 @@ extern "C" int ffn_ffmlp_create(int32_t num_hidden, int32_t num_channels, int32_
   }
   net->num_layers = nl;
   net->heads.push_back(PackHead{num_hidden, 256, 0, 4});   // final Linear 256 -> 4, no activation
-  if (finalize_net(net)) { ffn_net_destroy(net); return 1; }
+  if (finalize_net(net) || build_ffmlp_backward(net, num_hidden)) { ffn_net_destroy(net); return 1; }
   if (encoded) {
     cudaError_t e = cudaMalloc(&net->d_ffm_b, sizeof(float) * 3 * E);
     if (e == cudaSuccess) e = cudaMalloc(&net->d_ffm_a, sizeof(float) * E);

@@ -189,6 +189,48 @@ static int build_nerf_backward(ffn_net* net, int L) {
   return 0;
 }
 
+// backward program of a FourierFeatureMLP handle (fourier_feature_models.py:57-78): H hidden ReLU layers of
+// 256 and a final Linear 256 -> 4.  Slot i <-> hidden layer i (output h_{i+1}); layer 0's input is the
+// encoding, so the dgrad chain stops at dz_0.
+static int build_ffmlp_backward(ffn_net* net, int H) {
+  memset(net->layers_bwd, 0, sizeof(net->layers_bwd));
+  BwdPackArgs& bp = net->bwd_pack;
+  memset(&bp, 0, sizeof(bp));
+  uint32_t off = 0;
+  int nl = 0;
+  for (int i = H - 1; i >= 1; --i) {   // dh_i = dz_i . W_i, masked by relu'(h_i) -> dz_{i-1}
+    LayerDesc& ld = net->layers_bwd[nl];
+    ld.n = 256; ld.epi = EPI_BWD_MASK; ld.n_chunks = 4; ld.w_offset = off;
+    ld.mask_idx = (int8_t)(i - 1); ld.save_idx = (int8_t)(i - 1);
+    bp.L[nl].n_chunks = 4; bp.L[nl].w_offset = off;
+    for (int c = 0; c < 4; ++c) {
+      ld.src[c] = (uint8_t)c; ld.ksteps[c] = 4;
+      bp.L[nl].lin[c] = i; bp.L[nl].inf[c] = 256; bp.L[nl].koff[c] = c * 64; bp.L[nl].kcnt[c] = 64;
+    }
+    off += 256u * 128u * 4u;
+    ++nl;
+  }
+  bp.n_layers = nl;
+  net->num_layers_bwd = nl;
+  net->wpack_bwd_bytes = off;
+  if (off) {
+    CUDA_TRY(cudaMalloc(&net->d_wpack_bwd, off));
+    CUDA_TRY(cudaMemset(net->d_wpack_bwd, 0, off));
+  }
+  // forward save slots: the MMA layer that produces h_{i+1} (the two-pass first layer has a pseudo layer in front)
+  const int tp = net->num_layers - H;
+  for (int l = 0; l < net->num_layers; ++l) { net->layers[l].save_idx = -1; net->layers[l].mask_idx = -1; }
+  for (int i = 0; i < H; ++i) { net->layers[i + tp].save_idx = (int8_t)i; net->layers[i + tp].mask_idx = (int8_t)i; }
+  net->n_save = H; net->n_mask = H; net->n_dz = H;
+  net->bwd_first_cols = 256; net->bwd_first_heads = 4; net->bwd_first_mask = H - 1; net->bwd_first_save = H - 1;
+  net->bwd_sigma_chunk = 0;
+  net->trainable = true;
+  CUDA_TRY(cudaFuncSetAttribute(ffn_render_kernel<false, PASS_TRAIN_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+  CUDA_TRY(cudaFuncSetAttribute(ffn_render_kernel<true, PASS_TRAIN_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+  CUDA_TRY(cudaFuncSetAttribute(ffn_render_kernel<true, PASS_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+  return 0;
+}
+
 // ============================================================================================
 // C ABI
 // ============================================================================================
@@ -208,6 +250,7 @@ extern "C" int ffn_net_pack_backward(ffn_net_t* net, const float* const* weights
     if (!weights[i]) return fail("ffn_net_pack_backward: null weight pointer");
     pa.w[i] = weights[i];
   }
+  if (pa.n_layers == 0) return 0;
   dim3 grid(40, pa.n_layers);
   pack_weights_T_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(pa, net->d_wpack_bwd);
   g_launches += 1;
@@ -232,7 +275,7 @@ extern "C" int ffn_train_forward(ffn_net_t* net, const float* positions, const f
                                  int32_t* nan_flag, void* stream_) {
   if (!net || !net->trainable) return fail("ffn_train_forward: this net has no training program");
   if (R == 0) return 0;
-  if (!color || !alpha || !raw || !save_h || !save_mask || !save_enc || !nan_flag)
+  if (!color || !alpha || !raw || !save_h || !save_mask || !nan_flag || (net->kind == ENC_NERF && !save_enc))
     return fail("ffn_train_forward: null output/workspace pointer");
   const bool rays = starts != nullptr;
   if (rays ? (!directions || !near_ || !far_ || !lin || !t_out) : (!positions || !t_values))

@@ -46,8 +46,9 @@ class Raycaster(nn.Module):
         device = next(self.model.parameters()).device
         needs_grad = _needs_grad(self.model)
         fused = device.type == "cuda" and _engine.supported(self.model) and not needs_grad
-        if (device.type == "cuda" and needs_grad and getattr(self.model, "_ffn_kind", None) == "nerf"
-                and self.train_kernels):
+        kind = getattr(self.model, "_ffn_kind", None)
+        trainable = kind == "nerf" or (kind == "fourier" and self.model._engine_ok() and not self.model.keep_activations)
+        if device.type == "cuda" and needs_grad and trainable and self.train_kernels:
             from .autograd import render_nerf_train
             if isinstance(ray_samples, FocusBundle):     # t values come from the (frozen) coarse model
                 with torch.no_grad():

@@ -4,6 +4,8 @@ plain PyTorch definition of the same render (which equals the reference's, tests
 Tolerances (bf16 gradient operands, fp32 accumulation): per parameter cosine similarity >= 0.999 and
 relative L2 error <= 3e-2; compositing backward alone (fp32 end to end): <= 2e-5 relative.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -150,3 +152,62 @@ def test_inference_after_training_step_uses_new_weights():
     with torch.no_grad():
         after = rc.render(bundle, False).color
     assert (after - before).abs().max().item() > 1e-5
+
+
+@pytest.mark.parametrize("preset", ["mlp", "basic", "positional", "gaussian"])
+def test_ffmlp_gradients_match_fp32_autograd(preset):
+    """train_tiny_nerf.py's four FourierFeatureMLP presets through the training kernels."""
+    torch.manual_seed(4)
+    model = {"mlp": lambda: ffn.MLP(3, 4), "basic": lambda: ffn.BasicFourierMLP(3, 4),
+             "positional": lambda: ffn.PositionalFourierMLP(3, 4, 5.5),
+             "gaussian": lambda: ffn.GaussianFourierMLP(3, 4, 3.14)}[preset]()
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.requires_grad and name.endswith("weight"):
+                p.mul_(1.5)
+        model.layers[-1].weight.mul_(4.0)
+    model = model.to(DEV)
+    R, S = 128, 64
+    bundle = make_batch(R, S).to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    gt_c, gt_a = torch.rand((R, 3), device=DEV, generator=g), torch.rand((R,), device=DEV, generator=g)
+    rc = ffn.Raycaster(model)
+    rc.train_kernels = False
+    model.zero_grad()
+    loss_fn(rc.render(bundle, True), gt_c, gt_a).backward()
+    ref = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    rc.train_kernels = True
+    model.zero_grad()
+    before = _lib.launch_count()
+    out = rc.render(bundle, True)
+    loss_fn(out, gt_c, gt_a).backward()
+    assert _lib.launch_count() - before >= 3
+    for n, p in model.named_parameters():
+        if n not in ref:
+            continue
+        a, b = p.grad.flatten().double(), ref[n].flatten().double()
+        cos = (a @ b / (a.norm() * b.norm() + 1e-30)).item()
+        rel = ((a - b).norm() / (b.norm() + 1e-30)).item()
+        # bf16 operands: the 510/512-wide high-frequency encodings of layer 0 round hardest (5 % bar there)
+        assert cos >= 0.999 and rel <= (5e-2 if n.startswith("layers.0.") else 3e-2), (preset, n, cos, rel)
+
+
+def test_fit_on_device_resident_dataset(tmp_path):
+    """Raycaster.fit (ray_caster.py:248-376) on a synthetic NPZ with dataset + sampler tables in HBM."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    data = str(tmp_path / "toy.npz")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_synthetic_dataset.py"), data,
+                    "--resolution", "32", "--train", "8", "--val", "2", "--test", "1", "--steps", "64"],
+                   check=True, capture_output=True, timeout=300)
+    train = ffn.ImageDataset.load(data, "train", 64, True, True).to(DEV)
+    val = ffn.ImageDataset.load(data, "val", 64, True, False).to(DEV)
+    torch.manual_seed(0)
+    model = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True).to(DEV)
+    rc = ffn.Raycaster(model)
+    before = _lib.launch_count()
+    log = rc.fit(train, val, 512, 5e-4, 60, 0, 30, 0.1, 250000, 0, [ffn.EvaluationVisualizer(str(tmp_path), val, 30)])
+    assert _lib.launch_count() - before > 200          # the kernels did the work
+    assert len(log) >= 2 and log[-1].val_psnr > log[0].val_psnr, [e.val_psnr for e in log]
+    assert any(f.endswith(".png") for f in os.listdir(os.path.join(str(tmp_path), "val")))
