@@ -639,7 +639,23 @@ static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int 
     if (net->bf16) CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<true, PASS_TRAIN_FWD>, ka));
     else CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<false, PASS_TRAIN_FWD>, ka));
   } else if (net->bf16) CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<true, PASS_INFER>, ka));
-  else CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<false, PASS_INFER>, ka));
+  else {
+    // cta_group::2 variant (fp16 inference), read per launch so that one process can compare both kernels
+    const char* env_pair = getenv("FFN_PAIR");
+    bool use_pair = env_pair != nullptr && env_pair[0] == '1';
+    for (int l = 0; l < ka.num_layers; ++l) use_pair = use_pair && (ka.layers[l].n % 16 == 0);
+    if (use_pair) {
+      static bool attr_done = false;
+      if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(ffn_render_kernel<false, PASS_INFER, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+        attr_done = true;
+      }
+      CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<false, PASS_INFER, true>, ka));
+    } else {
+      CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<false, PASS_INFER>, ka));
+    }
+  }
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return 0;

@@ -200,6 +200,86 @@ __device__ __forceinline__ void umma_commit_warp_mc(uint32_t bar_mc, uint32_t ba
       : "memory");
 }
 
+// ---- cta_group::2 (one UMMA spans the two CTAs of a cluster: M = 256, each CTA holds its 128 rows of A,
+// half of B's N rows and its 128 rows of D) ---------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_chunk_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                   uint32_t accumulate, int ksteps) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pa, pt, p1, p2, p3;\n\t"
+      ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "setp.eq.u32 pt, 0, 0;\n\t"
+      "setp.gt.s32 p1, %5, 1;\n\t"
+      "setp.gt.s32 p2, %5, 2;\n\t"
+      "setp.gt.s32 p3, %5, 3;\n\t"
+      "and.pred p1, p1, pe;\n\t"
+      "and.pred p2, p2, pe;\n\t"
+      "and.pred p3, p3, pe;\n\t"
+      "add.u64 a1, %1, 2;  add.u64 b1, %2, 2;\n\t"
+      "add.u64 a2, %1, 4;  add.u64 b2, %2, 4;\n\t"
+      "add.u64 a3, %1, 6;  add.u64 b3, %2, 6;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, pa;\n\t"
+      "@p1 tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %3, pt;\n\t"
+      "@p2 tcgen05.mma.cta_group::2.kind::f16 [%0], a2, b2, %3, pt;\n\t"
+      "@p3 tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %3, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(ksteps)
+      : "memory");
+}
+// commit of cta_group::2 UMMAs, signalled at the same barrier offset in BOTH CTAs; bar1 (optional) likewise
+__device__ __forceinline__ void umma_commit_warp_pair(uint32_t bar0, uint32_t bar1) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, p1;\n\t"
+      ".reg .b16 m;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.u32 p1, %1, 0;\n\t"
+      "and.pred p1, p1, pe;\n\t"
+      "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t"
+      "@p1 tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%1], m;\n\t"
+      "}"
+      ::"r"(bar0), "r"(bar1)
+      : "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+// Instruction descriptor with M = 256 (cta_group::2)
+__device__ __forceinline__ uint32_t make_idesc_f16_m256(uint32_t n, bool bf16) {
+  uint32_t fmt = bf16 ? 1u : 0u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24);
+}
+
 // all previously issued tcgen05.mma of this thread -> arrive(1) on an mbarrier when complete
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)

@@ -246,9 +246,15 @@ __device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int b0,
 // ----------------------------------------------------------------------------------------
 // the kernel
 // ----------------------------------------------------------------------------------------
-template <bool kBF16, int kPass>
+// kPair: the two CTAs of the cluster execute every UMMA together (tcgen05 cta_group::2, M = 256): each CTA
+// supplies its own 128 rows of A and HALF of B's rows, so B operand reads, weight fills and the bytes the ring
+// must keep in flight all halve per SM.  Only rank 0's warp 1 issues; rank 1's warp 1 relays "my half of the
+// weight stage has landed" to rank 0.  Epilogues are unchanged (each CTA drains its own TMEM lanes).
+template <bool kBF16, int kPass, bool kPair = false>
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_render_kernel(const __grid_constant__ KernelArgs args) {
+  constexpr int kStages = kPair ? 4 : kWStages;
+  constexpr uint32_t kStageBytes = kPair ? kWStageBytes / 2 : kWStageBytes;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = ptx::smem_u32(smem);
   const int warp = threadIdx.x >> 5;
@@ -256,10 +262,11 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
 
   // misc region
   const uint32_t bars = smem_base + kSmemMisc;
-  const uint32_t bar_w_full = bars + 0;     // [2]
-  const uint32_t bar_w_empty = bars + 16;   // [2]
-  const uint32_t bar_a_ready = bars + 32;   // [2]
-  const uint32_t bar_acc_full = bars + 48;  // [2]
+  const uint32_t bar_w_full = bars + 0;     // [kStages <= 4]
+  const uint32_t bar_w_empty = bars + 32;   // [kStages <= 4]
+  const uint32_t bar_a_ready = bars + 64;   // [2]
+  const uint32_t bar_acc_full = bars + 80;  // [2]
+  const uint32_t cta_rank = ptx::cluster_ctarank();
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kSmemMisc + 128);
   float* scratch_base = reinterpret_cast<float*>(smem + kSmemMisc + 256);
 
@@ -269,10 +276,14 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
   }
 
   if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      // kPair: rank 0's "full" barrier also collects rank 1's relay arrive; "empty" comes from one multicast commit.
+      // !kPair: "empty" is released by the UMMA issuers of BOTH CTAs (multicast weight stream)
+      ptx::mbar_init(bar_w_full + 8 * i, (kPair && cta_rank == 0) ? 2 : 1);
+      ptx::mbar_init(bar_w_empty + 8 * i, kPair ? 1 : 2);
+    }
     for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(bar_w_full + 8 * i, 1);
-      ptx::mbar_init(bar_w_empty + 8 * i, 2);   // released by the UMMA issuers of BOTH CTAs of the cluster
-      ptx::mbar_init(bar_a_ready + 8 * i, kHelperWG ? 8 : 4);   // one arrive per epilogue warp
+      ptx::mbar_init(bar_a_ready + 8 * i, (kHelperWG ? 8 : 4) * (kPair ? 2 : 1));   // one arrive per epilogue warp
       ptx::mbar_init(bar_acc_full + 8 * i, 1);
     }
     ptx::fence_mbar_init();
@@ -285,8 +296,13 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
     ptx::fence_proxy_async();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), 512);
-    ptx::tmem_relinquish();
+    if constexpr (kPair) {
+      ptx::tmem_alloc_pair(ptx::smem_u32(tmem_ptr_smem), 512);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), 512);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -294,7 +310,6 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
   const uint32_t tmem_base = *tmem_ptr_smem;
   // 2-CTA cluster: each CTA fetches half of every weight chunk and multicasts it to both (halves the L2
   // traffic of the weight stream).  Nothing may reach the peer before its barriers are initialised.
-  const uint32_t cta_rank = ptx::cluster_ctarank();
   ptx::cluster_sync_all();
 
   // static round-robin tile schedule: local tile k of this CTA is global tile blockIdx.x + k*grid,
@@ -302,7 +317,10 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
   const int num_tiles = args.num_tiles;
   // every CTA runs the same number of iterations (the two CTAs of a cluster stream weights in lock step);
   // a tile index >= num_tiles simply has no valid row
-  const int my_tiles = (num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  // kPair: a "tile" of the schedule is a pair tile of 256 rows (128 per CTA), one stream per cluster
+  const int sched_units = kPair ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int sched_tiles = kPair ? (num_tiles + 1) / 2 : num_tiles;
+  const int my_tiles = (sched_tiles + sched_units - 1) / sched_units;
   const int L = args.num_layers;
 
   if (warp == 0) {
@@ -313,7 +331,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       for (int l = 0; l < L; ++l) {
         const LayerDesc& ld = args.layers[l];
         const uint32_t bytes = (uint32_t)ld.n * 128u;
-        const int npass = args.lockstep ? 1 : nslots;    // lock-step: one weight stream feeds both slots
+        const int npass = (!kPair && args.lockstep) ? 1 : nslots;    // lock-step: one weight stream feeds both slots
         for (int s = 0; s < npass; ++s) {
           // chunk -1 = the layer's bias tile (N x 32 B), then the weight K-chunks
           for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
@@ -322,14 +340,37 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
               const uint32_t nbytes = c < 0 ? (uint32_t)ld.n * 32u : bytes;
               const uint8_t* src = c < 0 ? args.wpack + ld.bias_off
                                          : args.wpack + ld.w_offset + (size_t)c * bytes;
-              const uint32_t hb = nbytes >> 1;      // my half, multicast to both CTAs
-              ptx::mbar_arrive_expect_tx(bar_w_full + 8 * stage, nbytes);
-              ptx::bulk_g2s_mc(smem_base + kSmemW + stage * kWStageBytes + cta_rank * hb, src + cta_rank * hb, hb,
-                               bar_w_full + 8 * stage, (uint16_t)3);
+              const uint32_t hb = nbytes >> 1;      // my half
+              if constexpr (kPair) {
+                // my half of B's rows stays in MY shared memory (cta_group::2 reads the other half from the peer)
+                ptx::mbar_arrive_expect_tx(bar_w_full + 8 * stage, hb);
+                ptx::bulk_g2s(smem_base + kSmemW + stage * kStageBytes, src + cta_rank * hb, hb, bar_w_full + 8 * stage);
+              } else {
+                // multicast my half to both CTAs
+                ptx::mbar_arrive_expect_tx(bar_w_full + 8 * stage, nbytes);
+                ptx::bulk_g2s_mc(smem_base + kSmemW + stage * kStageBytes + cta_rank * hb, src + cta_rank * hb, hb,
+                                 bar_w_full + 8 * stage, (uint16_t)3);
+              }
             }
             __syncwarp();
-            if (++stage == kWStages) { stage = 0; phase ^= 1u; }
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
+        }
+      }
+    }
+  } else if (warp == 1 && kPair && cta_rank != 0) {
+    // ================================================================ rank 1: weight-stage relay
+    uint32_t stage = 0, phase = 0;
+    for (int kp = 0; kp < my_tiles; kp += 2) {
+      const int nslots = min(2, my_tiles - kp);
+      for (int l = 0; l < L; ++l) {
+        const LayerDesc& ld = args.layers[l];
+        const int nst = nslots * (ld.n_chunks + (ld.has_bias ? 1 : 0));
+        for (int i = 0; i < nst; ++i) {
+          ptx::mbar_wait(bar_w_full + 8 * stage, phase);        // my half has landed in my shared memory
+          if (lane == 0) ptx::mbar_arrive_remote(bar_w_full + 8 * stage, 0u);
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -343,8 +384,8 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       const int nslots = min(2, my_tiles - kp);
       for (int l = 0; l < L; ++l) {
         const LayerDesc& ld = args.layers[l];
-        const uint32_t idesc = ptx::make_idesc_f16(ld.n, kBF16);
-        if (args.lockstep) {
+        const uint32_t idesc = kPair ? ptx::make_idesc_f16_m256(ld.n, kBF16) : ptx::make_idesc_f16(ld.n, kBF16);
+        if (!kPair && args.lockstep) {
           // ---- lock-step schedule: both slots run layer l together and share every weight stage
           long long t0 = prof ? clock64() : 0;
           for (int s = 0; s < nslots; ++s) {
@@ -382,7 +423,8 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
         }
         for (int s = 0; s < nslots; ++s) {
           long long t0 = prof ? clock64() : 0;
-          ptx::mbar_wait(bar_a_ready + 8 * s, a_phase[s]);
+          if constexpr (kPair) ptx::mbar_wait_cluster(bar_a_ready + 8 * s, a_phase[s]);   // arrivals from both CTAs
+          else ptx::mbar_wait(bar_a_ready + 8 * s, a_phase[s]);
           if (prof) t_wait_a += clock64() - t0;
           a_phase[s] ^= 1u;
           ptx::tc_fence_after();
@@ -391,25 +433,31 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           uint32_t accumulate = ld.accumulate;
           for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
             t0 = prof ? clock64() : 0;
-            ptx::mbar_wait(bar_w_full + 8 * stage, phase);
+            if constexpr (kPair) ptx::mbar_wait_cluster(bar_w_full + 8 * stage, phase);   // my half + the peer's relay
+            else ptx::mbar_wait(bar_w_full + 8 * stage, phase);
             if (prof) t_wait_w += clock64() - t0;
             ptx::tc_fence_after();
             {
               // whole (converged) warp, one elected lane issues: see ptx::umma_chunk_ss
-              const uint32_t b_addr = smem_base + kSmemW + stage * kWStageBytes;
-              if (c < 0) {
-                // D = ones(128x16) . bias_tile(Nx16)^T : every row of the accumulator starts at the bias
-                ptx::umma_chunk_ss(d_tmem, ptx::make_kmajor_nosw_desc(smem_base + kSmemOnes, 128u, 0u),
-                                   ptx::make_kmajor_nosw_desc(b_addr, kBiasTileLBO, kBiasTileSBO), idesc, accumulate, 1);
+              const uint32_t b_addr = smem_base + kSmemW + stage * kStageBytes;
+              const uint64_t a_desc = c < 0 ? ptx::make_kmajor_nosw_desc(smem_base + kSmemOnes, 128u, 0u)
+                                            : ptx::make_kmajor_sw128_desc(slot_base + (uint32_t)ld.src[c] * kChunkBytesA);
+              // c < 0: D = ones(128x16) . bias_tile(Nx16)^T : every row of the accumulator starts at the bias
+              const uint64_t b_desc = c < 0 ? ptx::make_kmajor_nosw_desc(b_addr, kBiasTileLBO, kBiasTileSBO)
+                                            : ptx::make_kmajor_sw128_desc(b_addr);
+              const int ks_n = c < 0 ? 1 : ld.ksteps[c];
+              const uint32_t full_bar = c == ld.n_chunks - 1 ? bar_acc_full + 8 * s : 0u;
+              if constexpr (kPair) {
+                ptx::umma_chunk_ss_pair(d_tmem, a_desc, b_desc, idesc, accumulate, ks_n);
+                ptx::umma_commit_warp_pair(bar_w_empty + 8 * stage, full_bar);
               } else {
-                ptx::umma_chunk_ss(d_tmem, ptx::make_kmajor_sw128_desc(slot_base + (uint32_t)ld.src[c] * kChunkBytesA),
-                                   ptx::make_kmajor_sw128_desc(b_addr), idesc, accumulate, ld.ksteps[c]);
+                ptx::umma_chunk_ss(d_tmem, a_desc, b_desc, idesc, accumulate, ks_n);
+                ptx::umma_commit_warp_mc(bar_w_empty + 8 * stage, full_bar);
               }
               accumulate = 1u;
-              ptx::umma_commit_warp_mc(bar_w_empty + 8 * stage, c == ld.n_chunks - 1 ? bar_acc_full + 8 * s : 0u);
             }
             __syncwarp();
-            if (++stage == kWStages) { stage = 0; phase ^= 1u; }
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -442,7 +490,9 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
     long long e_wait = 0, e_work = 0, e_front = 0, e_back = 0, e_t = 0;
 
     for (int k = slot; k < my_tiles; k += 2) {
-      const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
+      // kPair: pair tile (256 rows) of cluster blockIdx.x/2, this CTA owns rows [rank*128, rank*128+128)
+      const long long tile = kPair ? ((long long)(blockIdx.x >> 1) + (long long)k * (gridDim.x >> 1)) * 2 + cta_rank
+                                   : (long long)blockIdx.x + (long long)k * gridDim.x;
       const long long row_g = tile * kTileM + row;
       const bool valid = row_g < args.M;
       const long long e_t0 = eprof ? clock64() : 0;
@@ -555,7 +605,10 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(my_a_ready);
+      if (lane == 0) {
+        if (kPair && cta_rank != 0) ptx::mbar_arrive_remote(my_a_ready, 0u);   // the issuer lives in rank 0
+        else ptx::mbar_arrive(my_a_ready);
+      }
 
       float out[4] = {0.f, 0.f, 0.f, 0.f};  // raw rgb | sigma of this sample
 
@@ -682,7 +735,10 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           ptx::fence_proxy_async();
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(my_a_ready);
+          if (lane == 0) {
+            if (kPair && cta_rank != 0) ptx::mbar_arrive_remote(my_a_ready, 0u);
+            else ptx::mbar_arrive(my_a_ready);
+          }
         }
         if (ld.sigma_head) {
           // sigma_raw = w_op . h + b: add the helper's partial dot product (after the UMMA issuer was released)
@@ -790,7 +846,10 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync_all();     // the peer may still multicast into / commit onto this CTA's shared memory
-  if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+  if (warp == 2) {
+    if constexpr (kPair) ptx::tmem_dealloc_pair(tmem_base, 512);
+    else ptx::tmem_dealloc(tmem_base, 512);
+  }
 }
 
 }  // namespace ffn

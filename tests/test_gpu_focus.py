@@ -105,7 +105,9 @@ def test_focus_kernel_well_conditioned_vs_oracle(S):
     t2 = _lib.focus_t(cuda(raw_sigma), cuda(near), cuda(far), cuda(near_u), cuda(far_u),
                       torch.linspace(0, 1, n_f).to(DEV), torch.linspace(0, 1, n_u).to(DEV), None, None, True, 8, S)
     assert (t1[:, 1:] >= t1[:, :-1]).all() and not torch.equal(t1, t2)
-    assert (t1.min(1)[0].cpu().numpy() >= near - 1e-5).all() and (t1.max(1)[0].cpu().numpy() <= far + 1e-5).all()
+    # stratified samples may overshoot the segment end by one stratum (ray_sampler.py:380-386)
+    hi = np.maximum(far, far_u + (far_u - near_u) / n_u)
+    assert (t1.min(1)[0].cpu().numpy() >= near - 1e-5).all() and (t1.max(1)[0].cpu().numpy() <= hi + 1e-5).all()
 
 
 @pytest.mark.parametrize("S", [32, 128, 100])

@@ -1,0 +1,54 @@
+"""Compare the default render kernel with the cta_group::2 variant (FFN_PAIR=1): outputs and launch time.
+    timeout -s KILL 180 python tools/pair_probe.py
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import fourier_feature_nets_b200 as ffn  # noqa: E402
+from fourier_feature_nets_b200 import engine  # noqa: E402
+
+dev = torch.device("cuda:0")
+torch.manual_seed(20080524)
+model = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True).to(dev).eval()
+with torch.no_grad():
+    model.opacity_out.weight.mul_(20.0)
+eng = engine.get_engine(model, dev, "fp16")
+
+
+def run(R, S, iters):
+    gen = torch.Generator(device=dev).manual_seed(R)
+    o = torch.tensor([0.0, 0.3, -4.0], device=dev).repeat(R, 1)
+    d = torch.nn.functional.normalize(torch.randn((R, 3), device=dev, generator=gen) * 0.15
+                                      + torch.tensor([0, 0, 1.0], device=dev), dim=-1)
+    near = torch.full((R,), 3.0, device=dev)
+    far = torch.full((R,), 5.0, device=dev)
+    lin = torch.linspace(0, 1, S).to(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = None
+    for i in range(iters):
+        if i == iters - 1:
+            e0.record()
+        out = eng.net.render_rays(o, d, near, far, lin, None, True, 1, 0, S, True)
+    e1.record()
+    torch.cuda.synchronize()
+    return out, e0.elapsed_time(e1)
+
+
+for R, S in ((3, 64), (100, 64), (1000, 48), (4096, 64), (262144, 64)):
+    os.environ["FFN_PAIR"] = "0"
+    a, ms_a = run(R, S, 3)
+    os.environ["FFN_PAIR"] = "1"
+    b, ms_b = run(R, S, 3)
+    print("R=%d S=%d" % (R, S), flush=True)
+    for x, y, name in zip(a, b, ("color", "alpha", "depth")):
+        if x is None:
+            continue
+        print("   %s max|default - pair| = %.3g" % (name, (x - y).abs().max().item()), flush=True)
+    print("   default %.3f ms (%.2f M rays/s)   pair %.3f ms (%.2f M rays/s)" % (
+        ms_a, R / ms_a / 1e3, ms_b, R / ms_b / 1e3), flush=True)
+if os.environ.get("FFN_STATS"):
+    st = eng.net.debug_stats()
+    print("stats", st)
