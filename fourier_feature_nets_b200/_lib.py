@@ -93,6 +93,8 @@ def lib() -> ctypes.CDLL:
     L.ffn_composite.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p]
     L.ffn_blend_weights.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
+    L.ffn_generate_rays.argtypes = [c_void_p, c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
+                                    c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.ffn_focus_t.argtypes = [c_void_p, c_int32] + [c_void_p] * 9 + [c_int32, c_uint64, c_int64, c_int64, c_int32,
                                                                      c_void_p, c_void_p]
     L.ffn_focus_sample.argtypes = [c_void_p] + [c_void_p] * 11 + [c_int32, c_uint64, c_int64, c_int64, c_int32,
@@ -107,7 +109,7 @@ EXPORTED_SYMBOLS = [
     "ffn_version", "ffn_last_error", "ffn_nerf_create", "ffn_ffmlp_create", "ffn_net_destroy",
     "ffn_net_num_linear", "ffn_net_pack", "ffn_mlp_forward", "ffn_render_samples",
     "ffn_render_rays", "ffn_composite", "ffn_blend_weights", "ffn_debug_layer", "ffn_debug_stats", "ffn_launch_count",
-    "ffn_focus_t", "ffn_focus_sample", "ffn_render_rays_t",
+    "ffn_focus_t", "ffn_focus_sample", "ffn_render_rays_t", "ffn_generate_rays",
     "ffn_train_slots", "ffn_net_pack_backward", "ffn_train_forward", "ffn_composite_backward",
     "ffn_train_backward",
 ]
@@ -338,6 +340,26 @@ def blend_weights(t_values: torch.Tensor, opacity: torch.Tensor) -> torch.Tensor
     with torch.cuda.device(t.device):
         _check(lib().ffn_blend_weights(_ptr(t), _ptr(sg), R, S, _ptr(w), _stream()), "ffn_blend_weights")
     return w
+
+
+def generate_rays(unproj: torch.Tensor, cam_pos: torch.Tensor, bounds_min, bounds_max, width: int, height: int):
+    """``ffn_generate_rays``: per-camera inverse projections (C,4,4) and positions (C,3) on the device ->
+    ``starts (N,3), directions (N,3), near_far (2,N), valid (N) bool`` for the N = C*H*W pixel rays."""
+    u = _f32c(unproj.reshape(-1, 16), "unproj")
+    pos = _f32c(cam_pos.reshape(-1, 3), "cam_pos")
+    C = u.shape[0]
+    n = C * width * height
+    dev = u.device
+    starts = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    directions = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    near_far = torch.empty((2, n), dtype=torch.float32, device=dev)
+    valid = torch.empty((n,), dtype=torch.uint8, device=dev)
+    lo = (ctypes.c_float * 3)(*[float(v) for v in bounds_min])
+    hi = (ctypes.c_float * 3)(*[float(v) for v in bounds_max])
+    with torch.cuda.device(dev):
+        _check(lib().ffn_generate_rays(_ptr(u), _ptr(pos), lo, hi, C, width, height, _ptr(starts), _ptr(directions),
+                                       _ptr(near_far), _ptr(valid), _stream()), "ffn_generate_rays")
+    return starts, directions, near_far, valid.bool()
 
 
 def focus_t(raw_sigma: torch.Tensor, near, far, near_u, far_u, lin_c, lin_u, jitter_u, u_focus,

@@ -644,7 +644,16 @@ static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int 
     const char* env_pair = getenv("FFN_PAIR");
     bool use_pair = env_pair != nullptr && env_pair[0] == '1';
     for (int l = 0; l < ka.num_layers; ++l) use_pair = use_pair && (ka.layers[l].n % 16 == 0);
-    if (use_pair) {
+    const char* env_split = getenv("FFN_SPLIT");
+    if (use_pair && env_split != nullptr && env_split[0] == '1') {
+      static bool attr_done2 = false;
+      if (!attr_done2) {
+        CUDA_TRY(cudaFuncSetAttribute(ffn_render_kernel<false, PASS_INFER, true, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+        attr_done2 = true;
+      }
+      CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<false, PASS_INFER, true, true>, ka));
+    } else if (use_pair) {
       static bool attr_done = false;
       if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(ffn_render_kernel<false, PASS_INFER, true>,
@@ -794,3 +803,4 @@ extern "C" int ffn_debug_stats(ffn_net_t* net, uint64_t* out8) {
 #include "ffn_train.cuh"
 #include "ffn_ts_host.cuh"
 #include "ffn_focus.cuh"
+#include "ffn_raygen.cuh"

@@ -11,6 +11,7 @@ B200-first differences (same results, different plumbing):
 * ray tables may be made device-resident (``RaySampler.to(device)``), so indexing, the
   valid-ray filter and the image scatter are tensor ops instead of Python lists/sets.
 """
+import os
 from typing import List, NamedTuple, Optional, Union
 
 import numpy as np
@@ -177,7 +178,12 @@ class RaySampler:
 
     def __init__(self, bounds: np.ndarray, cameras: List[CameraInfo], num_samples: int,
                  stratified=False, opacity_model: nn.Module = None, batch_size=4096,
-                 anneal_start=0.5, num_anneal_steps=0):
+                 anneal_start=0.5, num_anneal_steps=0, device=None):
+        """Same arguments as the reference (ray_sampler.py:110-131) plus ``device``: a CUDA device (or the
+        ``FFN_RAY_DEVICE`` environment variable) builds the ray tables there with ``ffn_generate_rays`` instead
+        of numpy on the host (the reference spends ~0.75 s per 160 k rays in that loop)."""
+        if device is None and os.environ.get("FFN_RAY_DEVICE"):
+            device = os.environ["FFN_RAY_DEVICE"]
         self.bounds = bounds
         self.bounds_min = (bounds @ np.array([-0.5, -0.5, -0.5, 1], np.float32))[np.newaxis, :3]
         self.bounds_max = (bounds @ np.array([0.5, 0.5, 0.5, 1], np.float32))[np.newaxis, :3]
@@ -212,6 +218,10 @@ class RaySampler:
         self.points = np.stack([xs, ys], -1).reshape(-1, 2)
 
         num_focus = num_samples - (num_samples // 2)
+        self._invalid_set = None
+        if device is not None and torch.device(device).type == "cuda":
+            self._generate_on_device(torch.device(device), num_focus)
+            return
         starts, directions, near_far, cdfs, valid = [], [], [], [], []
         for camera in cameras:
             o, d = camera.raycast(self.points)
@@ -230,7 +240,23 @@ class RaySampler:
         self.valid_mask = torch.cat(valid)
         if self.focus_sampling and not self.lazy_focus:
             self.cdfs = torch.cat(cdfs)
-        self._invalid_set = None
+
+    def _generate_on_device(self, device: torch.device, num_focus: int):
+        """Ray tables straight into HBM: the 4x4 inverses are taken on the host
+        exactly like camera_info.py:101, everything per pixel runs in ``generate_rays_kernel``."""
+        from . import _lib
+        unproj = np.stack([np.linalg.inv(cam._projection()) for cam in self.cameras]).astype(np.float32)
+        pos = np.stack([np.asarray(cam.position, np.float32).reshape(3) for cam in self.cameras])
+        self.starts, self.directions, self.near_far, self.valid_mask = _lib.generate_rays(
+            torch.from_numpy(unproj).to(device), torch.from_numpy(pos).to(device), self.bounds_min[0],
+            self.bounds_max[0], self.image_width, self.image_height)
+        if self.focus_sampling and not self.lazy_focus:
+            cdfs = []
+            for lo in range(0, self.num_rays, self.rays_per_camera):
+                sl = slice(lo, lo + self.rays_per_camera)
+                t = linspace(self.near_far[0, sl], self.near_far[1, sl], num_focus)
+                cdfs.append(_determine_cdf(t, self._determine_opacity(t, self.starts[sl], self.directions[sl])))
+            self.cdfs = torch.cat(cdfs)
 
     # ---- device residency (section 8f-1): keep the ray tables in HBM ----------------------
     def to(self, device) -> "RaySampler":

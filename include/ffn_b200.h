@@ -141,6 +141,15 @@ int ffn_render_rays_t(ffn_net_t* net, const float* starts, const float* directio
                       int64_t num_rays, int32_t num_samples, float* color, float* alpha, float* depth,
                       int32_t* nan_flag, void* stream);
 
+/* ---- ray tables on the device: CameraInfo.unproject/raycast (camera_info.py:66-74,99-109) and
+ * RaySampler._near_far (ray_sampler.py:202-232) for every pixel of every camera.  unproj (C,16): row-major
+ * inv(K~ . inv(E)) per camera and cam_pos (C,3) are DEVICE pointers; bounds_min/bounds_max are HOST pointers to
+ * the 3 floats of bounds @ (-+.5,-+.5,-+.5,1).  Ray c*H*W + y*W + x is pixel (x,y) of camera c.  Outputs:
+ * starts, directions (C*H*W,3), near_far (2,C*H*W) [near clamped to >= 0.1 on hits], valid (C*H*W) bytes. ---- */
+int ffn_generate_rays(const float* unproj, const float* cam_pos, const float* bounds_min, const float* bounds_max,
+                      int32_t num_cameras, int32_t width, int32_t height, float* starts, float* directions,
+                      float* near_far, uint8_t* valid, void* stream);
+
 /* ---- training step (ray_caster.py:95-101,319-329): forward with saves, compositing backward, dgrad chain.
  * Weight gradients dW = dz^T x are plain GEMMs over the saved tensors and are left to the caller. ---- */
 
