@@ -206,7 +206,6 @@ __device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int b0,
                                                     uint32_t row7, __nv_bfloat16* gh, uint32_t* gm,
                                                     bool valid) {
   // this warpgroup converts the 32-column blocks [b0, b0 + nblk) of the layer (nblk = 8, 4 or 2)
-  uint32_t va[32], vb[32];
   uint32_t mwords[8];
   if constexpr (kPass == PASS_BWD && kMask) {
     const uint4 m0 = valid ? __ldg(reinterpret_cast<const uint4*>(gm)) : make_uint4(~0u, ~0u, ~0u, ~0u);
@@ -228,17 +227,16 @@ __device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int b0,
       }
     }
   };
-  ptx::tmem_ld32(taddr_base + (uint32_t)b0 * 32u, va);
+  // one x64 load (8 KB per warp) at a time: see ptx::tmem_ld64_wait.  4 warps x 8 KB in flight cover the
+  // ~260 cycle latency of the 64 B/clk TMEM read port, so the port stays busy while another warp converts
 #pragma unroll
   for (int i = 0; i < 8; i += 2) {
     if (i < nblk) {
       const int b = b0 + i;
-      ptx::tmem_wait_ld(va);
-      ptx::tmem_ld32(taddr_base + (uint32_t)(b + 1) * 32u, vb);
-      one(va, b);
-      ptx::tmem_wait_ld(vb);
-      if (i + 2 < nblk) ptx::tmem_ld32(taddr_base + (uint32_t)(b + 2) * 32u, va);
-      one(vb, b + 1);
+      uint32_t v[64];
+      ptx::tmem_ld64_wait(taddr_base + (uint32_t)b * 32u, v);
+      one(reinterpret_cast<uint32_t(&)[32]>(v[0]), b);
+      one(reinterpret_cast<uint32_t(&)[32]>(v[32]), b + 1);
     }
   }
 }
@@ -435,8 +433,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
         }
         for (int s = 0; s < nslots; ++s) {
           long long t0 = prof ? clock64() : 0;
-          if constexpr (kPair) ptx::mbar_wait_cluster(bar_a_ready + 8 * s, a_phase[s]);   // arrivals from both CTAs
-          else ptx::mbar_wait(bar_a_ready + 8 * s, a_phase[s]);
+          ptx::mbar_wait(bar_a_ready + 8 * s, a_phase[s]);   // kPair: arrivals from the epilogue warps of both CTAs
           if (prof) t_wait_a += clock64() - t0;
           a_phase[s] ^= 1u;
           ptx::tc_fence_after();

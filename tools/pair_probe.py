@@ -1,4 +1,5 @@
-"""Compare the default render kernel with the cta_group::2 variant (FFN_PAIR=1): outputs and launch time.
+"""Compare the render kernel variants: default (cta_group::1), pair (FFN_PAIR=1, cta_group::2) and
+pair + N-split (FFN_SPLIT=1): outputs against the default kernel and launch time.
     timeout -s KILL 180 python tools/pair_probe.py
 """
 import os
@@ -16,6 +17,7 @@ model = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True).to(dev).eval()
 with torch.no_grad():
     model.opacity_out.weight.mul_(20.0)
 eng = engine.get_engine(model, dev, "fp16")
+VARIANTS = (("default", "0", "0"), ("pair", "1", "0"), ("split", "1", "1"))
 
 
 def run(R, S, iters):
@@ -38,17 +40,17 @@ def run(R, S, iters):
 
 
 for R, S in ((3, 64), (100, 64), (1000, 48), (4096, 64), (262144, 64)):
-    os.environ["FFN_PAIR"] = "0"
-    a, ms_a = run(R, S, 3)
-    os.environ["FFN_PAIR"] = "1"
-    b, ms_b = run(R, S, 3)
     print("R=%d S=%d" % (R, S), flush=True)
-    for x, y, name in zip(a, b, ("color", "alpha", "depth")):
-        if x is None:
-            continue
-        print("   %s max|default - pair| = %.3g" % (name, (x - y).abs().max().item()), flush=True)
-    print("   default %.3f ms (%.2f M rays/s)   pair %.3f ms (%.2f M rays/s)" % (
-        ms_a, R / ms_a / 1e3, ms_b, R / ms_b / 1e3), flush=True)
-if os.environ.get("FFN_STATS"):
-    st = eng.net.debug_stats()
-    print("stats", st)
+    base = None
+    for name, pair, split in VARIANTS:
+        os.environ["FFN_PAIR"], os.environ["FFN_SPLIT"] = pair, split
+        out, ms = run(R, S, 3)
+        if base is None:
+            base = out
+        err = max((x - y).abs().max().item() for x, y in zip(base, out) if x is not None)
+        print("   %-8s %.3f ms (%.2f M rays/s)   max|x - default| = %.3g" % (name, ms, R / ms / 1e3, err), flush=True)
+        if os.environ.get("FFN_STATS") and R > 100000:
+            st = eng.net.debug_stats()
+            tot, wa, ww, n = st[:4]
+            print("      issuer: wait-epilogue %.1f%%  wait-weights %.1f%%  issuing %.1f%%" % (
+                100 * wa / tot, 100 * ww / tot, 100 * (tot - wa - ww) / tot), flush=True)
