@@ -593,6 +593,23 @@ extern "C" int ffn_net_pack(ffn_net_t* net, const float* const* weights, const f
 // ============================================================================================
 // launches
 // ============================================================================================
+// one instantiation of the render kernel; the opt-in to 227 KB of dynamic shared memory is set on first use
+template <bool kBF16, int kPass, bool kPair>
+static int launch_instance(const cudaLaunchConfig_t& cfg, const KernelArgs& ka) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(ffn_render_kernel<kBF16, kPass, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kSmemTotal));
+    attr_done = true;
+  }
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<kBF16, kPass, kPair>, ka));
+  return 0;
+}
+template <bool kBF16, int kPass>
+static int launch_variant(const cudaLaunchConfig_t& cfg, const KernelArgs& ka, bool pair) {
+  return pair ? launch_instance<kBF16, kPass, true>(cfg, ka) : launch_instance<kBF16, kPass, false>(cfg, ka);
+}
+
 static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int pass = PASS_INFER) {
   if (!net->packed) return fail("net has no packed weights: call ffn_net_pack first");
   if (ka.M <= 0) return 0;
@@ -634,36 +651,19 @@ static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int 
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (pass == PASS_BWD) CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<true, PASS_BWD>, ka));
-  else if (pass == PASS_TRAIN_FWD) {
-    if (net->bf16) CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<true, PASS_TRAIN_FWD>, ka));
-    else CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<false, PASS_TRAIN_FWD>, ka));
-  } else if (net->bf16) CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<true, PASS_INFER>, ka));
-  else {
-    // cta_group::2 variant (fp16 inference), read per launch so that one process can compare both kernels
-    const char* env_pair = getenv("FFN_PAIR");
-    bool use_pair = env_pair != nullptr && env_pair[0] == '1';
-    for (int l = 0; l < ka.num_layers; ++l) use_pair = use_pair && (ka.layers[l].n % 16 == 0);
-    const char* env_split = getenv("FFN_SPLIT");
-    if (use_pair && env_split != nullptr && env_split[0] == '1') {
-      static bool attr_done2 = false;
-      if (!attr_done2) {
-        CUDA_TRY(cudaFuncSetAttribute(ffn_render_kernel<false, PASS_INFER, true, true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-        attr_done2 = true;
-      }
-      CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<false, PASS_INFER, true, true>, ka));
-    } else if (use_pair) {
-      static bool attr_done = false;
-      if (!attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(ffn_render_kernel<false, PASS_INFER, true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-        attr_done = true;
-      }
-      CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<false, PASS_INFER, true>, ka));
-    } else {
-      CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<false, PASS_INFER>, ka));
-    }
+  // cta_group::2 ("pair") UMMAs are the default; FFN_PAIR=0 selects the single-CTA variant (read per launch so
+  // that one process can compare both).  A pair UMMA needs N % 16 == 0 in every layer.
+  const char* env_pair = getenv("FFN_PAIR");
+  bool pair = !(env_pair != nullptr && env_pair[0] == '0');
+  for (int l = 0; l < ka.num_layers; ++l) pair = pair && (ka.layers[l].n % 16 == 0);
+  if (pass == PASS_BWD) {
+    if (launch_variant<true, PASS_BWD>(cfg, ka, pair)) return 1;
+  } else if (pass == PASS_TRAIN_FWD) {
+    if (net->bf16 ? launch_variant<true, PASS_TRAIN_FWD>(cfg, ka, pair)
+                  : launch_variant<false, PASS_TRAIN_FWD>(cfg, ka, pair)) return 1;
+  } else {
+    if (net->bf16 ? launch_variant<true, PASS_INFER>(cfg, ka, pair)
+                  : launch_variant<false, PASS_INFER>(cfg, ka, pair)) return 1;
   }
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());

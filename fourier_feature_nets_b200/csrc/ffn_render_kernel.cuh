@@ -248,16 +248,14 @@ __device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int b0,
 // supplies its own 128 rows of A and HALF of B's rows, so B operand reads, weight fills and the bytes the ring
 // must keep in flight all halve per SM.  Only rank 0's warp 1 issues; rank 1's warp 1 relays "my half of the
 // weight stage has landed" to rank 0.  Epilogues are unchanged (each CTA drains its own TMEM lanes).
-// kSplit (with kPair): a 256-wide layer is accumulated as two N = 128 halves, all K chunks of columns [0,128)
-// first.  The epilogue drains half 0 while the tensor pipe still works on half 1, so only half a drain sits
-// between a slot's last UMMA and its next layer (the TMEM read port and the tensor pipe are both ~2100 cycles
-// per tile and layer; with whole-accumulator hand-offs they serialise).
-template <bool kBF16, int kPass, bool kPair = false, bool kSplit = false>
+// (Accumulating a 256-wide layer as two N = 128 halves so that half of the drain overlaps the second half's
+// UMMAs was tried and dropped: an SS-mode UMMA costs ~128 cycles whatever N is -- the 4 KB A operand read --
+// so the halves double the tensor time; profiles/r01_perf_experiments.md.)
+template <bool kBF16, int kPass, bool kPair = false>
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_render_kernel(const __grid_constant__ KernelArgs args) {
-  static_assert(!kSplit || kPair, "the split schedule is built on the pair kernel");
-  constexpr int kStages = kPair ? (kSplit ? 8 : 4) : kWStages;
-  constexpr uint32_t kStageBytes = kPair ? kWStageBytes / (kSplit ? 4 : 2) : kWStageBytes;
+  constexpr int kStages = kPair ? 4 : kWStages;
+  constexpr uint32_t kStageBytes = kPair ? kWStageBytes / 2 : kWStageBytes;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = ptx::smem_u32(smem);
   const int warp = threadIdx.x >> 5;
@@ -268,7 +266,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
   const uint32_t bar_w_full = bars + 0;      // [kStages <= 8]
   const uint32_t bar_w_empty = bars + 64;    // [kStages <= 8]
   const uint32_t bar_a_ready = bars + 128;   // [2 slots]
-  const uint32_t bar_acc_full = bars + 144;  // [2 slots][2 halves]: slot * 16 + half * 8
+  const uint32_t bar_acc_full = bars + 144;  // [2 slots], 16 bytes apart
   const uint32_t cta_rank = ptx::cluster_ctarank();
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kSmemMisc + 192);
   float* scratch_base = reinterpret_cast<float*>(smem + kSmemMisc + 256);
@@ -288,7 +286,6 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(bar_a_ready + 8 * i, (kHelperWG ? 8 : 4) * (kPair ? 2 : 1));   // one arrive per epilogue warp
       ptx::mbar_init(bar_acc_full + 16 * i, 1);
-      ptx::mbar_init(bar_acc_full + 16 * i + 8, 1);
     }
     ptx::fence_mbar_init();
   }
@@ -336,9 +333,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
         const LayerDesc& ld = args.layers[l];
         const uint32_t bytes = (uint32_t)ld.n * 128u;
         const int npass = (!kPair && args.lockstep) ? 1 : nslots;    // lock-step: one weight stream feeds both slots
-        const int nsplit = (kSplit && ld.n == 256) ? 2 : 1;
-        for (int sh = 0; sh < npass * nsplit; ++sh) {
-          const uint32_t h = (uint32_t)(sh % nsplit);                 // column half of the layer (kSplit)
+        for (int s = 0; s < npass; ++s) {
           // chunk -1 = the layer's bias tile (N x 32 B), then the weight K-chunks
           for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
             ptx::mbar_wait(bar_w_empty + 8 * stage, phase ^ 1u);
@@ -348,12 +343,10 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
                                          : args.wpack + ld.w_offset + (size_t)c * bytes;
               const uint32_t hb = nbytes >> 1;      // my half
               if constexpr (kPair) {
-                // my share of B's rows (of this column half) stays in MY shared memory; cta_group::2 reads the
-                // other CTA's rows from the peer.  Rows are contiguous in both the SW128 and the bias-tile layout.
-                const uint32_t qb = hb / (uint32_t)nsplit;
-                ptx::mbar_arrive_expect_tx(bar_w_full + 8 * stage, qb);
-                ptx::bulk_g2s(smem_base + kSmemW + stage * kStageBytes, src + (h * 2u + cta_rank) * qb, qb,
-                              bar_w_full + 8 * stage);
+                // my half of B's rows stays in MY shared memory; cta_group::2 reads the other half from the peer.
+                // Rows are contiguous in both the SW128 and the bias-tile layout.
+                ptx::mbar_arrive_expect_tx(bar_w_full + 8 * stage, hb);
+                ptx::bulk_g2s(smem_base + kSmemW + stage * kStageBytes, src + cta_rank * hb, hb, bar_w_full + 8 * stage);
               } else {
                 // multicast my half to both CTAs
                 ptx::mbar_arrive_expect_tx(bar_w_full + 8 * stage, nbytes);
@@ -374,7 +367,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       const int nslots = min(2, my_tiles - kp);
       for (int l = 0; l < L; ++l) {
         const LayerDesc& ld = args.layers[l];
-        const int nst = nslots * ((kSplit && ld.n == 256) ? 2 : 1) * (ld.n_chunks + (ld.has_bias ? 1 : 0));
+        const int nst = nslots * (ld.n_chunks + (ld.has_bias ? 1 : 0));
         for (int i = 0; i < nst; ++i) {
           ptx::mbar_wait(bar_w_full + 8 * stage, phase);        // my half has landed in my shared memory
           if (lane == 0) ptx::mbar_arrive_remote_relaxed(bar_w_full + 8 * stage, 0u);
@@ -393,8 +386,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       const int nslots = min(2, my_tiles - kp);
       for (int l = 0; l < L; ++l) {
         const LayerDesc& ld = args.layers[l];
-        const int nsplit = (kSplit && ld.n == 256) ? 2 : 1;
-        const uint32_t idesc = kPair ? ptx::make_idesc_f16_m256(ld.n / nsplit, kBF16) : ptx::make_idesc_f16(ld.n, kBF16);
+        const uint32_t idesc = kPair ? ptx::make_idesc_f16_m256(ld.n, kBF16) : ptx::make_idesc_f16(ld.n, kBF16);
         if (!kPair && args.lockstep) {
           // ---- lock-step schedule: both slots run layer l together and share every weight stage
           long long t0 = prof ? clock64() : 0;
@@ -438,8 +430,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           a_phase[s] ^= 1u;
           ptx::tc_fence_after();
           const uint32_t slot_base = smem_base + kSmemSlot0 + s * kSlotBytes;
-          for (int h = 0; h < nsplit; ++h) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)s * 256u + (uint32_t)h * 128u;
+          const uint32_t d_tmem = tmem_base + (uint32_t)s * 256u;
           uint32_t accumulate = ld.accumulate;
           for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
             t0 = prof ? clock64() : 0;
@@ -457,7 +448,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
               const uint64_t b_desc = c < 0 ? ptx::make_kmajor_nosw_desc(b_addr, kBiasTileLBO, kBiasTileSBO)
                                             : ptx::make_kmajor_sw128_desc(b_addr);
               const int ks_n = c < 0 ? 1 : ld.ksteps[c];
-              const uint32_t full_bar = c == ld.n_chunks - 1 ? bar_acc_full + 16 * s + 8 * h : 0u;
+              const uint32_t full_bar = c == ld.n_chunks - 1 ? bar_acc_full + 16 * s : 0u;
               if constexpr (kPair) {
                 ptx::umma_chunk_ss_pair(d_tmem, a_desc, b_desc, idesc, accumulate, ks_n);
                 ptx::umma_commit_warp_pair(bar_w_empty + 8 * stage, full_bar);
@@ -469,7 +460,6 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
             }
             __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
-          }
           }
         }
       }
@@ -492,10 +482,10 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
     const uint32_t enc_row_addr = slot_base + kEncChunk * kChunkBytesA + row_off;
     const uint32_t taddr_base = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)slot * 256u;
     const uint32_t my_a_ready = bar_a_ready + 8 * slot;
-    const uint32_t my_acc_full = bar_acc_full + 16 * slot;     // + 8 * column half
+    const uint32_t my_acc_full = bar_acc_full + 16 * slot;
     float* sc_t = scratch_base + slot * 320;       // [128] t values of the tile
     float* sc_part = sc_t + 128;                   // [4][8] per-warp partials
-    uint32_t acc_phase[2] = {0u, 0u};
+    uint32_t acc_phase = 0;
     const int S = args.S;
     const bool eprof = args.stats != nullptr && warp == 4 && lane == 0;
     float* sc_sig = sc_part + 32;                  // [128] helper's partial sigma head
@@ -627,22 +617,18 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       if (eprof) { const long long n = clock64(); e_front += n - e_t0; e_t = n; }
       for (int l = 0; l < L; ++l) {
         const LayerDesc& ld = args.layers[l];
-        const int nsplit = (kSplit && ld.n == 256) ? 2 : 1;   // column halves with their own "accumulator full"
         const int nblk_all = ld.n >> 5;                 // 32-column blocks of this layer (8 or 4)
-        const int nblk_grp = kHelperWG ? nblk_all >> 1 : nblk_all / nsplit;   // ... converted per warpgroup / half
+        const int nblk_grp = kHelperWG ? nblk_all >> 1 : nblk_all;   // ... converted by this warpgroup
         const bool general = ld.epi == EPI_RELU_HEAD || ld.sigma_head || args.dbg_layer == l;
-        float hacc[4] = {0.f, 0.f, 0.f, 0.f};
-        const int hn = ld.epi == EPI_RELU_HEAD ? ld.head_n : 0;   // heads 0..hn-1 (rgb | rgb+sigma)
-        for (int h = 0; h < nsplit; ++h) {
-        ptx::mbar_wait(my_acc_full + 8 * h, acc_phase[h]);
-        acc_phase[h] ^= 1u;
+        ptx::mbar_wait(my_acc_full, acc_phase);
+        acc_phase ^= 1u;
         ptx::tc_fence_after();
         if (eprof) { const long long n = clock64(); e_wait += n - e_t; e_t = n; }
 
-        const int blk0 = kHelperWG ? grp * nblk_grp : h * nblk_grp;
+        const int blk0 = grp * nblk_grp;
         if (ld.epi == EPI_ENC_PART2) {
           // wide FourierFeatureMLP encodings: features [160, 256) -> act chunks 0..2
-          if (grp == 0 && h == nsplit - 1)
+          if (grp == 0)
             write_enc_ffmlp<kBF16>(slot_base + row_off, row7, px, py, pz, args.ffm_b, args.ffm_a, args.emb, 160, 3);
         } else if (ld.epi == EPI_BWD_LINEAR || ld.epi == EPI_BWD_MASK) {
           if constexpr (kPass == PASS_BWD) {
@@ -672,10 +658,12 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           // general path: fp32 values are needed (sigma / rgb heads on CUDA cores, debug dump)
           const bool relu = ld.epi != EPI_LINEAR_ACT;
           const bool to_act = ld.epi != EPI_RELU_HEAD;
-          // helper warpgroup: output-head layers are converted by the primary warpgroup alone (their fp32 dot
-          // products stay in one thread); everything else is split between primary and helper
-          const int gb0 = (kHelperWG && hn > 0) ? 0 : blk0;
-          const int gb1 = (kHelperWG && hn > 0) ? (grp == 0 ? nblk_all : 0) : blk0 + nblk_grp;
+          float hacc[4] = {0.f, 0.f, 0.f, 0.f};
+          const int hn = ld.epi == EPI_RELU_HEAD ? ld.head_n : 0;   // heads 0..hn-1 (rgb | rgb+sigma)
+          // output-head layers are converted by the primary warpgroup alone (their fp32 dot products stay in
+          // one thread); everything else is split between primary and helper
+          const int gb0 = hn > 0 ? 0 : blk0;
+          const int gb1 = hn > 0 ? (grp == 0 ? nblk_all : 0) : blk0 + nblk_grp;
           for (int b = gb0; b < gb1; ++b) {
             uint32_t v[32];
             ptx::tmem_ld32(taddr_base + (uint32_t)b * 32u, v);
@@ -732,9 +720,6 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
               }
             }
           }
-        }
-        }   // column halves
-        if (general && ld.epi != EPI_ENC_PART2 && ld.epi != EPI_BWD_LINEAR && ld.epi != EPI_BWD_MASK) {
           if (ld.sigma_head) out[3] = hacc[3];      // partial over this warpgroup's columns, combined below
 #pragma unroll
           for (int o = 0; o < 4; ++o)

@@ -323,10 +323,10 @@ def test_full_size_properties(golden_nerf):
     eng.net.nan_flag() == 0
 
 
-@pytest.mark.parametrize("env", [{"FFN_USE_TS": "1"}, {"FFN_LOCKSTEP": "1"}, {"FFN_PAIR": "1"}])
+@pytest.mark.parametrize("env", [{"FFN_USE_TS": "1"}, {"FFN_PAIR": "0", "FFN_LOCKSTEP": "1"}, {"FFN_PAIR": "0"}])
 def test_alternative_kernel_schedules_stay_parity_green(env):
-    """The evaluated-but-not-default variants (A operand in TMEM; lock-step weight sharing; cta_group::2 pair
-    UMMAs) are selected by environment variables read at the first launch: run them in a fresh process."""
+    """The evaluated-but-not-default variants (A operand in TMEM; single-CTA UMMAs with and without lock-step
+    weight sharing) are selected by environment variables read at the first launch: run them in a fresh process."""
     import subprocess
     import sys
     from conftest import ROOT

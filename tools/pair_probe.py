@@ -1,5 +1,5 @@
-"""Compare the render kernel variants: default (cta_group::1), pair (FFN_PAIR=1, cta_group::2) and
-pair + N-split (FFN_SPLIT=1): outputs against the default kernel and launch time.
+"""Compare the render kernel variants: cta_group::1 (FFN_PAIR=0) and pair (cta_group::2): outputs against
+the cta_group::1 kernel and launch time.
     timeout -s KILL 180 python tools/pair_probe.py
 """
 import os
@@ -17,7 +17,7 @@ model = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True).to(dev).eval()
 with torch.no_grad():
     model.opacity_out.weight.mul_(20.0)
 eng = engine.get_engine(model, dev, "fp16")
-VARIANTS = (("default", "0", "0"), ("pair", "1", "0"), ("split", "1", "1"))
+VARIANTS = (("default", "0"), ("pair", "1"))
 
 
 def run(R, S, iters):
@@ -42,8 +42,8 @@ def run(R, S, iters):
 for R, S in ((3, 64), (100, 64), (1000, 48), (4096, 64), (262144, 64)):
     print("R=%d S=%d" % (R, S), flush=True)
     base = None
-    for name, pair, split in VARIANTS:
-        os.environ["FFN_PAIR"], os.environ["FFN_SPLIT"] = pair, split
+    for name, pair in VARIANTS:
+        os.environ["FFN_PAIR"] = pair
         out, ms = run(R, S, 3)
         if base is None:
             base = out
