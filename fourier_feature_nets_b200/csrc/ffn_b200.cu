@@ -631,8 +631,7 @@ static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int 
   ka.f_pos = net->f_pos; ka.f_view = net->f_view; ka.include_inputs = net->include_inputs;
   ka.use_view = net->use_view; ka.emb = net->emb; ka.ffm_a = net->d_ffm_a; ka.ffm_b = net->d_ffm_b;
   ka.bf16 = net->bf16;
-  static const int env_dbg_flags = getenv("FFN_DBG_FLAGS") ? atoi(getenv("FFN_DBG_FLAGS")) : 0;
-  ka.dbg_flags = env_dbg_flags;
+  ka.dbg_flags = getenv("FFN_DBG_FLAGS") ? atoi(getenv("FFN_DBG_FLAGS")) : 0;   // bring-up / timing experiments
   static const bool env_stats = getenv("FFN_STATS") != nullptr;
   ka.stats = env_stats ? net->d_stats : nullptr;
   static const int env_lockstep = getenv("FFN_LOCKSTEP") ? atoi(getenv("FFN_LOCKSTEP")) : 0;

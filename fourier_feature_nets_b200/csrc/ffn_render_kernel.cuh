@@ -491,6 +491,94 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
     float* sc_sig = sc_part + 32;                  // [128] helper's partial sigma head
     long long e_wait = 0, e_work = 0, e_front = 0, e_back = 0, e_t = 0;
 
+    // outputs of one finished tile: raw rows and / or the fused compositing (ray_caster.py:67-93 + utils.py:72-97).
+    // Deferred: it runs while this warpgroup would otherwise wait for the NEXT tile's second accumulator
+    auto finish_tile = [&](const float (&o)[4], float tv, int si, long long ry, long long rg, bool vld) {
+      if constexpr (kPass == PASS_BWD) return;
+      const long long e_t1 = eprof ? clock64() : 0;
+      if (vld && args.raw && (!args.fused || kPass == PASS_TRAIN_FWD))
+        reinterpret_cast<float4*>(args.raw)[rg] = make_float4(o[0], o[1], o[2], o[3]);
+      if (!args.fused) return;
+
+      // ray_caster.py:67-93 + utils.py:72-97, one thread per sample, S | 128
+      const float cr = sigmoid_f(o[0]), cg = sigmoid_f(o[1]), cb = sigmoid_f(o[2]);
+      const float sigma = softplus_f(o[3]);
+      if (vld && (isnan(cr) || isnan(cg) || isnan(cb) || isnan(sigma))) atomicOr(args.nan_flag, 1);
+      const uint32_t bar_id = 1 + slot;
+      sc_t[row] = tv;
+      ptx::named_bar_sync(bar_id, 128);
+      const bool last = si == S - 1;
+      const float delta = last ? 1e10f : __fsub_rn(sc_t[min(row + 1, 127)], tv);
+      const float al = __fsub_rn(1.f, expf(-__fmul_rn(sigma, delta)));
+      const float tr = fminf(1.f, __fadd_rn(__fsub_rn(1.f, al), 1e-10f));
+      // exclusive product scan over the samples of the ry
+      const int seg = S < 32 ? S : 32;
+      const int sl = lane & (seg - 1);
+      float inc = tr;
+      for (int off = 1; off < seg; off <<= 1) {
+        const float o = __shfl_up_sync(0xffffffffu, inc, off);
+        if (sl >= off) inc *= o;
+      }
+      float T = __shfl_up_sync(0xffffffffu, inc, 1);
+      if (sl == 0) T = 1.f;
+      const int wpr = S >> 5;  // warps per ry (0 when S < 32)
+      if (wpr > 1) {
+        if (lane == 31) sc_part[wq * 8 + 7] = inc;
+        ptx::named_bar_sync(bar_id, 128);
+        const int w0 = wq & ~(wpr - 1);
+        for (int w = w0; w < wq; ++w) T *= sc_part[w * 8 + 7];
+      }
+      const float wgt = al * T;
+      // reductions over the ry: sum(w c) over all samples, sum(w) and first argmax(w) over s < S-1
+      float r0 = wgt * cr, r1 = wgt * cg, r2 = wgt * cb, r3 = last ? 0.f : wgt;
+      float bw = last ? -1.f : wgt;
+      int bs = si;
+      for (int off = seg >> 1; off > 0; off >>= 1) {
+        r0 += __shfl_xor_sync(0xffffffffu, r0, off);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, off);
+        r2 += __shfl_xor_sync(0xffffffffu, r2, off);
+        r3 += __shfl_xor_sync(0xffffffffu, r3, off);
+        const float ow = __shfl_xor_sync(0xffffffffu, bw, off);
+        const int os = __shfl_xor_sync(0xffffffffu, bs, off);
+        if (ow > bw || (ow == bw && os < bs)) { bw = ow; bs = os; }
+      }
+      if (wpr > 1) {
+        if (lane == 0) {
+          sc_part[wq * 8 + 0] = r0; sc_part[wq * 8 + 1] = r1; sc_part[wq * 8 + 2] = r2;
+          sc_part[wq * 8 + 3] = r3; sc_part[wq * 8 + 4] = bw; sc_part[wq * 8 + 5] = __int_as_float(bs);
+        }
+        ptx::named_bar_sync(bar_id, 128);
+        if (si == 0) {
+          r0 = r1 = r2 = r3 = 0.f; bw = -2.f; bs = 0;
+          for (int w = wq; w < wq + wpr; ++w) {
+            r0 += sc_part[w * 8 + 0]; r1 += sc_part[w * 8 + 1]; r2 += sc_part[w * 8 + 2];
+            r3 += sc_part[w * 8 + 3];
+            const float ow = sc_part[w * 8 + 4];
+            const int os = __float_as_int(sc_part[w * 8 + 5]);
+            if (ow > bw || (ow == bw && os < bs)) { bw = ow; bs = os; }
+          }
+        }
+      }
+      if (vld && si == 0) {
+        args.rgb[ry * 3 + 0] = r0;
+        args.rgb[ry * 3 + 1] = r1;
+        args.rgb[ry * 3 + 2] = r2;
+        args.alpha[ry] = r3;
+        if (args.depth) {
+          const int cut = (r3 < 0.1f || S == 1) ? S - 1 : bs;   // ray_caster.py:86-89
+          args.depth[ry] = sc_t[row + cut];
+        }
+      }
+      // sc_t / sc_part are rewritten by the next tile only after its first named barrier
+      ptx::named_bar_sync(bar_id, 128);
+      if (eprof) e_back += clock64() - e_t1;
+    };
+    bool pend = false;                              // a finished tile whose outputs are still to be written
+    float p_out[4] = {0.f, 0.f, 0.f, 0.f}, p_tval = 0.f;
+    int p_sidx = 0;
+    long long p_ray = 0, p_row_g = 0;
+    bool p_valid = false;
+
     for (int k = slot; k < my_tiles; k += 2) {
       // kPair: pair tile (256 rows) of cluster blockIdx.x/2, this CTA owns rows [rank*128, rank*128+128)
       const long long tile = kPair ? ((long long)(blockIdx.x >> 1) + (long long)k * (gridDim.x >> 1)) * 2 + cta_rank
@@ -743,6 +831,11 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
             else ptx::mbar_arrive(my_a_ready);
           }
         }
+        if (l == 0 && pend && grp == 0) {
+          // the previous tile of this slot: composite it now, under the tensor core's work on layer 1
+          finish_tile(p_out, p_tval, p_sidx, p_ray, p_row_g, p_valid);
+          pend = false;
+        }
         if (ld.sigma_head) {
           // sigma_raw = w_op . h + b: add the helper's partial dot product (after the UMMA issuer was released)
           if constexpr (kHelperWG) {
@@ -756,87 +849,17 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       }
       ptx::tc_fence_before();
       if (grp != 0) continue;
-      const long long e_t1 = eprof ? clock64() : 0;
-
-      // ------------------------------------------------ outputs
-      if constexpr (kPass == PASS_BWD) continue;
-      if (valid && args.raw && (!args.fused || kPass == PASS_TRAIN_FWD))
-        reinterpret_cast<float4*>(args.raw)[row_g] = make_float4(out[0], out[1], out[2], out[3]);
-      if (!args.fused) continue;
-
-      // ray_caster.py:67-93 + utils.py:72-97, one thread per sample, S | 128
-      const float cr = sigmoid_f(out[0]), cg = sigmoid_f(out[1]), cb = sigmoid_f(out[2]);
-      const float sigma = softplus_f(out[3]);
-      if (valid && (isnan(cr) || isnan(cg) || isnan(cb) || isnan(sigma))) atomicOr(args.nan_flag, 1);
-      const uint32_t bar_id = 1 + slot;
-      sc_t[row] = tval;
-      ptx::named_bar_sync(bar_id, 128);
-      const bool last = sidx == S - 1;
-      const float delta = last ? 1e10f : __fsub_rn(sc_t[min(row + 1, 127)], tval);
-      const float al = __fsub_rn(1.f, expf(-__fmul_rn(sigma, delta)));
-      const float tr = fminf(1.f, __fadd_rn(__fsub_rn(1.f, al), 1e-10f));
-      // exclusive product scan over the samples of the ray
-      const int seg = S < 32 ? S : 32;
-      const int sl = lane & (seg - 1);
-      float inc = tr;
-      for (int off = 1; off < seg; off <<= 1) {
-        const float o = __shfl_up_sync(0xffffffffu, inc, off);
-        if (sl >= off) inc *= o;
+      // hand the tile to finish_tile(), called after the next tile's first layer (or after the loop)
+      if (pend) finish_tile(p_out, p_tval, p_sidx, p_ray, p_row_g, p_valid);   // single-layer programs only
+      pend = true;
+      p_out[0] = out[0]; p_out[1] = out[1]; p_out[2] = out[2]; p_out[3] = out[3];
+      p_tval = tval; p_sidx = sidx; p_ray = ray; p_row_g = row_g; p_valid = valid;
+      if (args.dbg_flags & 8) {          // timing experiments: composite at the end of the tile
+        finish_tile(p_out, p_tval, p_sidx, p_ray, p_row_g, p_valid);
+        pend = false;
       }
-      float T = __shfl_up_sync(0xffffffffu, inc, 1);
-      if (sl == 0) T = 1.f;
-      const int wpr = S >> 5;  // warps per ray (0 when S < 32)
-      if (wpr > 1) {
-        if (lane == 31) sc_part[wq * 8 + 7] = inc;
-        ptx::named_bar_sync(bar_id, 128);
-        const int w0 = wq & ~(wpr - 1);
-        for (int w = w0; w < wq; ++w) T *= sc_part[w * 8 + 7];
-      }
-      const float wgt = al * T;
-      // reductions over the ray: sum(w c) over all samples, sum(w) and first argmax(w) over s < S-1
-      float r0 = wgt * cr, r1 = wgt * cg, r2 = wgt * cb, r3 = last ? 0.f : wgt;
-      float bw = last ? -1.f : wgt;
-      int bs = sidx;
-      for (int off = seg >> 1; off > 0; off >>= 1) {
-        r0 += __shfl_xor_sync(0xffffffffu, r0, off);
-        r1 += __shfl_xor_sync(0xffffffffu, r1, off);
-        r2 += __shfl_xor_sync(0xffffffffu, r2, off);
-        r3 += __shfl_xor_sync(0xffffffffu, r3, off);
-        const float ow = __shfl_xor_sync(0xffffffffu, bw, off);
-        const int os = __shfl_xor_sync(0xffffffffu, bs, off);
-        if (ow > bw || (ow == bw && os < bs)) { bw = ow; bs = os; }
-      }
-      if (wpr > 1) {
-        if (lane == 0) {
-          sc_part[wq * 8 + 0] = r0; sc_part[wq * 8 + 1] = r1; sc_part[wq * 8 + 2] = r2;
-          sc_part[wq * 8 + 3] = r3; sc_part[wq * 8 + 4] = bw; sc_part[wq * 8 + 5] = __int_as_float(bs);
-        }
-        ptx::named_bar_sync(bar_id, 128);
-        if (sidx == 0) {
-          r0 = r1 = r2 = r3 = 0.f; bw = -2.f; bs = 0;
-          for (int w = wq; w < wq + wpr; ++w) {
-            r0 += sc_part[w * 8 + 0]; r1 += sc_part[w * 8 + 1]; r2 += sc_part[w * 8 + 2];
-            r3 += sc_part[w * 8 + 3];
-            const float ow = sc_part[w * 8 + 4];
-            const int os = __float_as_int(sc_part[w * 8 + 5]);
-            if (ow > bw || (ow == bw && os < bs)) { bw = ow; bs = os; }
-          }
-        }
-      }
-      if (valid && sidx == 0) {
-        args.rgb[ray * 3 + 0] = r0;
-        args.rgb[ray * 3 + 1] = r1;
-        args.rgb[ray * 3 + 2] = r2;
-        args.alpha[ray] = r3;
-        if (args.depth) {
-          const int cut = (r3 < 0.1f || S == 1) ? S - 1 : bs;   // ray_caster.py:86-89
-          args.depth[ray] = sc_t[row + cut];
-        }
-      }
-      // sc_t / sc_part are rewritten by the next tile only after its first named barrier
-      ptx::named_bar_sync(bar_id, 128);
-      if (eprof) e_back += clock64() - e_t1;
     }
+    if (pend) finish_tile(p_out, p_tval, p_sidx, p_ray, p_row_g, p_valid);
     if (eprof) {
       atomicAdd(args.stats + 4, (unsigned long long)e_wait);
       atomicAdd(args.stats + 5, (unsigned long long)e_work);

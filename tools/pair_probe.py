@@ -1,5 +1,6 @@
-"""Compare the render kernel variants: cta_group::1 (FFN_PAIR=0) and pair (cta_group::2): outputs against
-the cta_group::1 kernel and launch time.
+"""Compare the render kernel variants: cta_group::1 (FFN_PAIR=0), pair (cta_group::2, the default) and pair with
+the compositing at the end of each tile (FFN_DBG_FLAGS=8): outputs against the cta_group::1 kernel, launch time
+and -- the stable A/B signal, wall time moves with the power cap -- issuer-warp cycles (FFN_STATS=1).
     timeout -s KILL 180 python tools/pair_probe.py
 """
 import os
@@ -17,7 +18,7 @@ model = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True).to(dev).eval()
 with torch.no_grad():
     model.opacity_out.weight.mul_(20.0)
 eng = engine.get_engine(model, dev, "fp16")
-VARIANTS = (("default", "0"), ("pair", "1"))
+VARIANTS = (("single", "0", "0"), ("pair", "1", "0"), ("pair/nodefer", "1", "8"))
 
 
 def run(R, S, iters):
@@ -42,15 +43,15 @@ def run(R, S, iters):
 for R, S in ((3, 64), (100, 64), (1000, 48), (4096, 64), (262144, 64)):
     print("R=%d S=%d" % (R, S), flush=True)
     base = None
-    for name, pair in VARIANTS:
-        os.environ["FFN_PAIR"] = pair
+    for name, pair, flags in VARIANTS:
+        os.environ["FFN_PAIR"], os.environ["FFN_DBG_FLAGS"] = pair, flags
         out, ms = run(R, S, 3)
         if base is None:
             base = out
         err = max((x - y).abs().max().item() for x, y in zip(base, out) if x is not None)
-        print("   %-8s %.3f ms (%.2f M rays/s)   max|x - default| = %.3g" % (name, ms, R / ms / 1e3, err), flush=True)
+        print("   %-13s %.3f ms (%.2f M rays/s)   max|x - default| = %.3g" % (name, ms, R / ms / 1e3, err), flush=True)
         if os.environ.get("FFN_STATS") and R > 100000:
             st = eng.net.debug_stats()
             tot, wa, ww, n = st[:4]
-            print("      issuer: wait-epilogue %.1f%%  wait-weights %.1f%%  issuing %.1f%%" % (
-                100 * wa / tot, 100 * ww / tot, 100 * (tot - wa - ww) / tot), flush=True)
+            print("      issuer: %.0f cycles/CTA  wait-epilogue %.1f%%  wait-weights %.1f%%  issuing %.1f%%" % (
+                tot / n, 100 * wa / tot, 100 * ww / tot, 100 * (tot - wa - ww) / tot), flush=True)
