@@ -302,7 +302,7 @@ class Net:
         return color, alpha, depth
 
     def debug_stats(self):
-        out = (ctypes.c_uint64 * 8)()
+        out = (ctypes.c_uint64 * 32)()
         lib().ffn_debug_stats.argtypes = [c_void_p, c_void_p]
         _check(lib().ffn_debug_stats(self.handle, out), "ffn_debug_stats")
         return list(out)

@@ -337,8 +337,8 @@ static int finalize_net(ffn_net* net) {
                       cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&net->d_cparams, sizeof(ConstParams)));
   CUDA_TRY(cudaMemset(net->d_cparams, 0, sizeof(ConstParams)));
-  CUDA_TRY(cudaMalloc(&net->d_stats, 8 * sizeof(unsigned long long)));
-  CUDA_TRY(cudaMemset(net->d_stats, 0, 8 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&net->d_stats, 32 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(net->d_stats, 0, 32 * sizeof(unsigned long long)));
   if (g_num_sms == 0) {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -791,11 +791,11 @@ extern "C" int ffn_blend_weights(const float* t_values, const float* opacity, in
   return 0;
 }
 
-extern "C" int ffn_debug_stats(ffn_net_t* net, uint64_t* out8) {
-  if (!net || !out8) return fail("ffn_debug_stats: null argument");
+extern "C" int ffn_debug_stats(ffn_net_t* net, uint64_t* out32) {
+  if (!net || !out32) return fail("ffn_debug_stats: null argument");
   CUDA_TRY(cudaDeviceSynchronize());
-  CUDA_TRY(cudaMemcpy(out8, net->d_stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemset(net->d_stats, 0, 8 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemcpy(out32, net->d_stats, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemset(net->d_stats, 0, 32 * sizeof(unsigned long long)));
   return 0;
 }
 

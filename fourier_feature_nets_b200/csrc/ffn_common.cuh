@@ -128,7 +128,7 @@ struct KernelArgs {
   int32_t dbg_layer;
   int32_t dbg_flags;           // bit 0: swap LBO/SBO roles of the no-swizzle descriptors (bring-up aid)
   float* dbg_out;              // (M,256)
-  unsigned long long* stats;   // optional [8]: issuer-warp cycle counters (FFN_STATS=1), see ffn_debug_stats
+  unsigned long long* stats;   // optional [32]: cycle counters (FFN_STATS=1), see ffn_debug_stats
   // training (PASS_TRAIN_FWD writes, PASS_BWD reads masks / writes dz)
   __nv_bfloat16* save_h;       // [n_save][M][256] layer outputs (bf16, post-activation)
   uint32_t* save_mask;         // [n_mask][M][8]   ReLU sign words (bit 31-j of word b <-> column 32b+j is <= 0)

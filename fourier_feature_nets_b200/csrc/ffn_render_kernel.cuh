@@ -201,10 +201,13 @@ __device__ __forceinline__ void apply_sign_mask(uint32_t (&v)[32], uint32_t w) {
 //   kPass = PASS_INFER      store only
 //   kPass = PASS_TRAIN_FWD  + bf16 copy to gh, sign words to gm (when kRelu)
 //   kPass = PASS_BWD        kMask: multiply by ReLU' from the sign words at gm; A tile and HBM copy in bf16
-template <bool kBF16, bool kRelu, int kPass, bool kMask>
+//   kSigma: additionally the fp32 dot product of the activated row with head 3 (opacity_out, nerf_model.py:117)
+//           into *hsum, columns in ascending order; needs b0 == 0 as a literal so that the weights become
+//           constant-bank operands of the FFMAs
+template <bool kBF16, bool kRelu, int kPass, bool kMask, bool kSigma = false>
 __device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int b0, int nblk, uint32_t act_row,
                                                     uint32_t row7, __nv_bfloat16* gh, uint32_t* gm,
-                                                    bool valid) {
+                                                    bool valid, float* hsum = nullptr) {
   // this warpgroup converts the 32-column blocks [b0, b0 + nblk) of the layer (nblk = 8, 4 or 2)
   uint32_t mwords[8];
   if constexpr (kPass == PASS_BWD && kMask) {
@@ -216,6 +219,13 @@ __device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int b0,
   auto one = [&](uint32_t (&v)[32], int b) {
     const uint32_t chunk_row = act_row + (uint32_t)(b >> 1) * kChunkBytesA;
     const uint32_t u0 = (uint32_t)(b & 1) * 4u;
+    if constexpr (kSigma) {
+      float a = *hsum;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        a = fmaf(kRelu ? fmaxf(__uint_as_float(v[j]), 0.f) : __uint_as_float(v[j]), c_params.head_w[3][b * 32 + j], a);
+      *hsum = a;
+    }
     if constexpr (kPass == PASS_BWD) {
       if constexpr (kMask) apply_sign_mask(v, mwords[b]);
       store_act_block<true, false>(v, chunk_row, row7, u0);
@@ -237,6 +247,30 @@ __device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int b0,
       ptx::tmem_ld64_wait(taddr_base + (uint32_t)b * 32u, v);
       one(reinterpret_cast<uint32_t(&)[32]>(v[0]), b);
       one(reinterpret_cast<uint32_t(&)[32]>(v[32]), b + 1);
+    }
+  }
+}
+
+// Output-head layer (EPI_RELU_HEAD, inference): ReLU of the accumulator, then the kHn fp32 dot products of
+// color_out / the final Linear (nerf_model.py:122, fourier_feature_models.py:77) straight from the registers;
+// nothing is written back.  Fully unrolled so that the head weights are constant-bank operands of the FFMAs
+// (the generic path below indexes them dynamically: an LDC per element, 4x slower); per head the columns are
+// accumulated in ascending order, exactly like the generic path.
+template <int kHn>
+__device__ __forceinline__ void head_layer_epilogue(uint32_t taddr_base, int nblk, float (&hacc)[4]) {
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    if (i < nblk) {
+      uint32_t v[64];
+      ptx::tmem_ld64_wait(taddr_base + (uint32_t)i * 32u, v);
+#pragma unroll
+      for (int o = 0; o < kHn; ++o) {
+        float a = hacc[o];
+#pragma unroll
+        for (int j = 0; j < 64; ++j)
+          a = fmaf(fmaxf(__uint_as_float(v[j]), 0.f), c_params.head_w[o][i * 32 + j], a);
+        hacc[o] = a;
+      }
     }
   }
 }
@@ -728,6 +762,32 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
             else
               lean_layer_epilogue<true, false, PASS_BWD, false>(taddr_base, blk0, nblk_grp, slot_base + row_off, row7, gh, gm, valid);
           }
+        } else if (kPass == PASS_INFER && ld.epi == EPI_RELU_HEAD && !ld.sigma_head && args.dbg_layer != l &&
+                   (ld.head_n == 3 || ld.head_n == 4) && (nblk_all & 1) == 0) {
+          // output heads on CUDA cores, unrolled
+          float hacc[4] = {0.f, 0.f, 0.f, 0.f};
+          if (grp == 0) {
+            if (ld.head_n == 3) head_layer_epilogue<3>(taddr_base, nblk_all, hacc);
+            else head_layer_epilogue<4>(taddr_base, nblk_all, hacc);
+          }
+#pragma unroll
+          for (int o = 0; o < 4; ++o)
+            if (o < ld.head_n) out[o] = hacc[o] + c_params.head_b[o];
+        } else if (!kHelperWG && ld.sigma_head && ld.epi == EPI_RELU_ACT && args.dbg_layer != l && ld.n == 256) {
+          // trunk layer that also feeds opacity_out: the lean path plus one fp32 dot product
+          const size_t rg = valid ? (size_t)row_g : 0;
+          __nv_bfloat16* gh = nullptr;
+          uint32_t* gm = nullptr;
+          if constexpr (kPass == PASS_TRAIN_FWD) {
+            if (ld.save_idx >= 0) gh = args.save_h + ((size_t)ld.save_idx * args.M + rg) * 256;
+            if (ld.mask_idx >= 0) gm = args.save_mask + ((size_t)ld.mask_idx * args.M + rg) * 8;
+          }
+          if constexpr (kPass != PASS_BWD) {
+            constexpr int kP = kPass == PASS_TRAIN_FWD ? PASS_TRAIN_FWD : PASS_INFER;
+            float hs = 0.f;
+            lean_layer_epilogue<kBF16, true, kP, false, true>(taddr_base, 0, 8, slot_base + row_off, row7, gh, gm, valid, &hs);
+            out[3] = hs;          // + head_b[3] below
+          }
         } else if (!general) {
           // lean path (the bias is already in the accumulator)
           const size_t rg = valid ? (size_t)row_g : 0;
@@ -845,7 +905,12 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           }
           if (grp == 0) out[3] += c_params.head_b[3];
         }
-        if (eprof) { const long long n = clock64(); e_work += n - e_t; e_t = n; }
+        if (eprof) {
+          const long long n = clock64();
+          e_work += n - e_t;
+          if (l < 24) atomicAdd(args.stats + 8 + l, (unsigned long long)(n - e_t));
+          e_t = n;
+        }
       }
       ptx::tc_fence_before();
       if (grp != 0) continue;

@@ -184,10 +184,11 @@ int ffn_train_backward(ffn_net_t* net, const float* d_raw, const void* save_mask
 int ffn_debug_layer(ffn_net_t* net, const float* positions, const float* views, int64_t n,
                     int32_t layer, float* out256, void* stream);
 
-/* Debug: with FFN_STATS=1 in the environment the render kernel's UMMA-issuer warps accumulate
- * {total cycles, cycles waiting for the epilogue, cycles waiting for weights, CTAs}; this reads
- * (after a device sync) and clears them. */
-int ffn_debug_stats(ffn_net_t* net, uint64_t* out8);
+/* Debug: with FFN_STATS=1 in the environment the render kernel accumulates 32 cycle counters: [0..3] UMMA-issuer
+ * warps {total, waiting for the epilogue, waiting for weights, issuer count}, [4..7] epilogue warp 4 of every
+ * CTA {waiting for the accumulator, converting, tile front (inputs + encoding), compositing}, [8..31] the
+ * converting time split by layer.  This reads (after a device sync) and clears them. */
+int ffn_debug_stats(ffn_net_t* net, uint64_t* out32);
 
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t ffn_launch_count(void);

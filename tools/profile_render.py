@@ -47,5 +47,9 @@ if os.environ.get("FFN_STATS"):
     if st[4] + st[5]:
         print("epilogue warp 4 (per CTA, cycles): wait-acc %.0f  convert+store %.0f  front(enc) %.0f  back(composite) %.0f" % (
             st[4] / n, st[5] / n, st[6] / n, st[7] / n))
+    # counters [8 + l]: summed over warp 4 (slot 0) of all 148 CTAs and over all launches
+    tiles_per_slot = args.iters * R * S / 128 / 2
+    print("epilogue cycles per tile and layer (acc-full -> A-ready):",
+          " ".join("%.0f" % (x / tiles_per_slot) for x in st[8:8 + 12]))
     print("issuer warp: total %.0f cyc/CTA, wait-epilogue %.1f%%, wait-weights %.1f%%, issuing %.1f%%" % (
         tot / n, 100 * wa / tot, 100 * ww / tot, 100 * (tot - wa - ww) / tot))
