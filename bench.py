@@ -124,6 +124,15 @@ def measured_peak():
     return 1590.0, "fallback 1.59 PFLOP/s (B200_PROFILING.md)"
 
 
+def sustained_peak():
+    """cuBLAS bf16 TFLOP/s inside a long step (the bench step is one ~65 ms launch under the power cap)."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops_sustained"])
+    except Exception:
+        return None
+
+
 def ncu_traffic():
     """dram bytes per launch of the render kernel from the committed ncu capture, if any."""
     path = os.path.join(ROOT, "profiles", "ncu_render_kernel.json")
@@ -288,6 +297,7 @@ def main():
                        "jitter": "in-kernel Philox4x32-10"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "peak_source": peak_src + " (of measured)",
+                         "frac_of_sustained": None if sustained_peak() is None else achieved / sustained_peak(),
                          # ncu (one --set full capture) measured dram bytes for a launch of
                          # `rays_per_launch` rays; traffic scales linearly with the rays of a launch
                          "traffic": None if traffic is None else
@@ -327,6 +337,32 @@ def main():
                 "value": n / cpu_s, "unit": "rays/s", "cores": cores, "kind": "port",
                 "sample": "%d rays x %d samples of the same workload, numpy oracle, host cores: %d"
                           % (n, SAMPLES, os.cpu_count())}
+            # the reference's op sequence (RaySamples -> NeRF.forward -> compositing, ray_caster.py:48-93) as plain
+            # fp32 PyTorch on the SAME GPU, inference batches of 4096 rays like orbit_video.py:37 -- the "1-GPU
+            # PyTorch" denominator of north_star's >= 10x target.  Bounded sample, device-resident inputs.
+            with torch.no_grad():
+                tb = 4096
+                nb = 16
+                mats = [dev_bundles[W].subset(range(i * tb, (i + 1) * tb)).materialize() for i in range(nb)]
+                model.forward = model.forward_torch      # plain PyTorch layers instead of the CUDA engine
+                try:
+                    launches_t = _lib.launch_count()
+                    ref_t = rc._render_torch(mats[0], True)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for m in mats:
+                        rc._render_torch(m, True)
+                    torch.cuda.synchronize()
+                    torch_s = time.perf_counter() - t0
+                    assert _lib.launch_count() == launches_t, "torch baseline must not touch libffn_b200"
+                finally:
+                    del model.forward
+                ours_t = rc.render(dev_bundles[W].subset(range(0, tb)).materialize(), True)
+            line["torch_gpu_baseline"] = {
+                "value": nb * tb / torch_s, "unit": "rays/s",
+                "sample": "%d batches of %d rays x %d samples, plain fp32 PyTorch ops of the reference definition on "
+                          "the same GPU, samples already materialised in HBM" % (nb, tb, SAMPLES),
+                "color_max_abs_vs_ours": float((ours_t.color - ref_t.color).abs().max())}
             line["parity"] = {"rays": n, "color_max_abs": float(err.max()),
                               "alpha_max_abs": float(np.abs(ours.alpha - ref.alpha).max()),
                               "depth_mismatch_frac": float((ours.depth != ref.depth).mean()),
