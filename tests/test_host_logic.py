@@ -267,3 +267,58 @@ def test_image_dataset_sample_cameras_and_npz_load(tmp_path):
     assert tr.num_cameras == 3 and va.num_cameras == 1 and tr.cameras[2].name == "train002"
     img = va.to_image(0, np.ones((len(va.index_for_camera(0)), 3), np.float32))
     assert img.shape == (20, 20, 3) and img.max() == 255
+
+
+# ---- checkpoint fidelity: .pt files written by the real reference ----------------
+def test_checkpoints_written_by_the_reference_load_and_reproduce():
+    g = load("checkpoints.npz")
+    pos, view = torch.from_numpy(g["pos"]), torch.from_numpy(g["view"])
+    nerf = ffn.load_model(os.path.join(GOLDEN, "ref_nerf_small.pt"))
+    four = ffn.load_model(os.path.join(GOLDEN, "ref_fourier_small.pt"))
+    assert isinstance(nerf, ffn.NeRF) and isinstance(four, ffn.FourierFeatureMLP)
+    with torch.no_grad():
+        np.testing.assert_allclose(nerf(pos, view).numpy(), g["out_nerf"], atol=2e-6)
+        np.testing.assert_allclose(four(pos).numpy(), g["out_fourier"], atol=2e-6)
+    # what our save() writes has the reference's layout: same keys, same "type"/"params" entries
+    for name, model in (("ref_nerf_small.pt", nerf), ("ref_fourier_small.pt", four)):
+        ref_raw = torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=False)
+        sd = model.state_dict()
+        ours = dict(sd, type=ref_raw["type"], params=model.params)
+        assert list(ours.keys()) == list(ref_raw.keys())
+        assert set(ours["params"].keys()) == set(ref_raw["params"].keys())
+        for k, v in ref_raw["params"].items():
+            mine = ours["params"][k]
+            if isinstance(v, (torch.Tensor, np.ndarray, list)) and not isinstance(v, (str,)) and v is not None \
+                    and not isinstance(v, bool):
+                np.testing.assert_allclose(np.asarray(mine, dtype=np.float64), np.asarray(v, dtype=np.float64))
+            else:
+                assert mine == v, (k, mine, v)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/fourier_feature_nets"), reason="needs the reference checkout")
+def test_our_checkpoints_load_in_the_reference(tmp_path):
+    import subprocess
+    import sys
+    m = ffn.NeRF(4, 32, 5, 3, 2, 2, [2], True)
+    f = ffn.GaussianFourierMLP(3, 4, 2.5, num_layers=2, num_channels=32, embedding_size=16)
+    m.save(str(tmp_path / "n.pt"))
+    f.save(str(tmp_path / "f.pt"))
+    x = torch.rand((16, 3)) * 2 - 1
+    with torch.no_grad():
+        np.savez(str(tmp_path / "exp.npz"), x=x.numpy(), n=m(x, x).numpy(), f=f(x).numpy())
+    code = r"""
+import sys, os, numpy as np, torch
+sys.path.insert(0, %r)
+from make_golden import import_reference
+ref = import_reference()
+e = np.load(%r)
+x = torch.from_numpy(e["x"])
+n = ref.load_model(%r); f = ref.load_model(%r)
+assert type(n).__module__.startswith("fourier_feature_nets.") and type(n).__name__ == "NeRF"
+with torch.no_grad():
+    assert np.abs(n(x, x).numpy() - e["n"]).max() <= 2e-6
+    assert np.abs(f(x).numpy() - e["f"]).max() <= 2e-6
+print("OK")
+""" % (GOLDEN, str(tmp_path / "exp.npz"), str(tmp_path / "n.pt"), str(tmp_path / "f.pt"))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "OK" in res.stdout, res.stdout[-500:] + res.stderr[-1500:]
