@@ -15,6 +15,7 @@ from .ray_dataset_modes import Mode
 from .ray_sampler import FocusBundle, RayBundle, RaySampler, RaySamples
 from .utils import (ETABar, RenderResult, calculate_blend_weights, exponential_lr_decay, linspace,
                     load_model, orbit)
+from .voxels_model import Voxels
 from .visualizers import (ActivationVisualizer, ComparisonVisualizer, EvaluationVisualizer,
                           OrbitVideoVisualizer)
 
@@ -26,4 +27,4 @@ __all__ = ["CameraInfo", "Resolution", "MLP", "NeRF", "BasicFourierMLP", "Fourie
            "PositionalFourierMLP", "GaussianFourierMLP", "Raycaster", "RayCaster", "RaySampler",
            "RaySamples", "RayBundle", "FocusBundle", "RenderResult", "Mode", "ImageDataset", "RayDataset", "calculate_blend_weights",
            "exponential_lr_decay", "linspace", "load_model", "orbit", "ETABar", "EvaluationVisualizer",
-           "OrbitVideoVisualizer", "ActivationVisualizer", "ComparisonVisualizer", "__version__"]
+           "OrbitVideoVisualizer", "ActivationVisualizer", "ComparisonVisualizer", "Voxels", "__version__"]

@@ -95,6 +95,8 @@ def lib() -> ctypes.CDLL:
     L.ffn_blend_weights.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
     L.ffn_generate_rays.argtypes = [c_void_p, c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
                                     c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.ffn_voxels_forward.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_float), c_int32, c_float, c_void_p, c_int64,
+                                     c_void_p, c_void_p]
     L.ffn_focus_t.argtypes = [c_void_p, c_int32] + [c_void_p] * 9 + [c_int32, c_uint64, c_int64, c_int64, c_int32,
                                                                      c_void_p, c_void_p]
     L.ffn_focus_sample.argtypes = [c_void_p] + [c_void_p] * 11 + [c_int32, c_uint64, c_int64, c_int64, c_int32,
@@ -109,7 +111,7 @@ EXPORTED_SYMBOLS = [
     "ffn_version", "ffn_last_error", "ffn_nerf_create", "ffn_ffmlp_create", "ffn_net_destroy",
     "ffn_net_num_linear", "ffn_net_pack", "ffn_mlp_forward", "ffn_render_samples",
     "ffn_render_rays", "ffn_composite", "ffn_blend_weights", "ffn_debug_layer", "ffn_debug_stats", "ffn_launch_count",
-    "ffn_focus_t", "ffn_focus_sample", "ffn_render_rays_t", "ffn_generate_rays",
+    "ffn_focus_t", "ffn_focus_sample", "ffn_render_rays_t", "ffn_generate_rays", "ffn_voxels_forward",
     "ffn_train_slots", "ffn_net_pack_backward", "ffn_train_forward", "ffn_composite_backward",
     "ffn_train_backward",
 ]
@@ -360,6 +362,19 @@ def generate_rays(unproj: torch.Tensor, cam_pos: torch.Tensor, bounds_min, bound
         _check(lib().ffn_generate_rays(_ptr(u), _ptr(pos), lo, hi, C, width, height, _ptr(starts), _ptr(directions),
                                        _ptr(near_far), _ptr(valid), _stream()), "ffn_generate_rays")
     return starts, directions, near_far, valid.bool()
+
+
+def voxels_forward(grid_channels_last: torch.Tensor, bias4, scale: float, positions: torch.Tensor) -> torch.Tensor:
+    """``ffn_voxels_forward``: (side,side,side,4) grid on the device, 4 bias floats, positions (N,3) -> (N,4)."""
+    g = _f32c(grid_channels_last, "grid")
+    p = _f32c(positions.reshape(-1, 3), "positions")
+    n = p.shape[0]
+    out = torch.empty((n, 4), dtype=torch.float32, device=p.device)
+    b = (ctypes.c_float * 4)(*[float(v) for v in bias4])
+    with torch.cuda.device(p.device):
+        _check(lib().ffn_voxels_forward(_ptr(g), b, g.shape[0], float(scale), _ptr(p), n, _ptr(out), _stream()),
+               "ffn_voxels_forward")
+    return out
 
 
 def focus_t(raw_sigma: torch.Tensor, near, far, near_u, far_u, lin_c, lin_u, jitter_u, u_focus,

@@ -144,10 +144,28 @@ class FocusBundle(RayBundle):
         S = self.num_samples
         n_u, n_f = S // 2, S - S // 2
         dev = self.starts.device
-        eng = _engine.get_engine(self.coarse_model, dev)
-        return eng.net.focus_sample(self.starts, self.directions, self.near_raw, self.far_raw, self.near, self.far,
-                                    torch.linspace(0, 1, n_f).to(dev), torch.linspace(0, 1, n_u).to(dev),
-                                    self.jitter, self.u_focus, self.stratified, self.seed, S)
+        lin_c, lin_u = torch.linspace(0, 1, n_f).to(dev), torch.linspace(0, 1, n_u).to(dev)
+        model = self.coarse_model
+        if _engine.supported(model) and getattr(model, "use_view", False):
+            eng = _engine.get_engine(model, dev)
+            return eng.net.focus_sample(self.starts, self.directions, self.near_raw, self.far_raw, self.near,
+                                        self.far, lin_c, lin_u, self.jitter, self.u_focus, self.stratified,
+                                        self.seed, S)
+        # any other opacity model on the device (e.g. ``Voxels``): its own forward gives the coarse raw outputs at
+        # t_c = linspace(near, far, S_c) (ray_sampler.py:246-263), the CDF / inverse transform / sort run in
+        # ``ffn_focus_t``
+        from . import _lib
+        n = len(self.near_raw)
+        t_c = self.near_raw.unsqueeze(-1) + lin_c.unsqueeze(0) * (self.far_raw - self.near_raw).unsqueeze(-1)
+        dirs = self.directions.reshape(n, 1, 3)
+        pos = (self.starts.reshape(n, 1, 3) + t_c.unsqueeze(-1) * dirs).reshape(-1, 3)
+        with torch.no_grad():
+            if getattr(model, "use_view", False):
+                raw = model(pos, dirs.expand(-1, n_f, -1).reshape(-1, 3))
+            else:
+                raw = model(pos)
+        return _lib.focus_t(raw.reshape(n, n_f, -1)[..., -1].contiguous(), self.near_raw, self.far_raw, self.near,
+                            self.far, lin_c, lin_u, self.jitter, self.u_focus, self.stratified, self.seed, S)
 
     def materialize(self) -> RaySamples:
         if self._cache is None:
@@ -198,15 +216,13 @@ class RaySampler:
         self.stratified = stratified
         self.opacity_model = opacity_model
         self.focus_sampling = opacity_model is not None
-        # an opacity model the CUDA engine can evaluate is sampled lazily, per batch, on the GPU: no
+        # an opacity model that lives on a CUDA device is sampled lazily, per batch, on the GPU: no
         # constructor-time sigma pass over every ray, no (num_rays, S_c-1) CDF table
         self.lazy_focus = False
         if self.focus_sampling:
             self.opacity_model.eval()
-            from . import engine as _engine
             params = list(self.opacity_model.parameters())
-            self.lazy_focus = bool(_engine.supported(self.opacity_model) and params and params[0].is_cuda
-                                   and getattr(self.opacity_model, "use_view", False))
+            self.lazy_focus = bool(params and params[0].is_cuda)
         self.batch_size = batch_size
         self.seed = 20080524
         self._draws = 0

@@ -80,6 +80,9 @@ def load_model(path: str) -> torch.nn.Module:
         model = FourierFeatureMLP(**params)
     elif kind == "nerf":
         model = NeRF(**params)
+    elif kind == "voxels":
+        from .voxels_model import Voxels
+        model = Voxels(**params)
     else:
         raise ValueError("Unrecognized model type: %s" % kind)
     model.load_state_dict(state)

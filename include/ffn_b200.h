@@ -150,6 +150,12 @@ int ffn_generate_rays(const float* unproj, const float* cam_pos, const float* bo
                       int32_t num_cameras, int32_t width, int32_t height, float* starts, float* directions,
                       float* near_far, uint8_t* valid, void* stream);
 
+/* Voxels.forward (voxels_model.py:35-45): trilinear grid_sample (border padding, align_corners=False) of
+ * positions / scale + bias.  grid_channels_last: DEVICE (side,side,side,4) = voxels[0].permute(1,2,3,0);
+ * bias4: HOST pointer to 4 floats; positions (n,3) and out4 (n,4) DEVICE. */
+int ffn_voxels_forward(const float* grid_channels_last, const float* bias4, int32_t side, float scale,
+                       const float* positions, int64_t n, float* out4, void* stream);
+
 /* ---- training step (ray_caster.py:95-101,319-329): forward with saves, compositing backward, dgrad chain.
  * Weight gradients dW = dz^T x are plain GEMMs over the saved tensors and are left to the caller. ---- */
 

@@ -279,8 +279,12 @@ def test_checkpoints_written_by_the_reference_load_and_reproduce():
     with torch.no_grad():
         np.testing.assert_allclose(nerf(pos, view).numpy(), g["out_nerf"], atol=2e-6)
         np.testing.assert_allclose(four(pos).numpy(), g["out_fourier"], atol=2e-6)
+    vox = ffn.load_model(os.path.join(GOLDEN, "ref_voxels_small.pt"))
+    assert isinstance(vox, ffn.Voxels) and vox.use_view is False
+    with torch.no_grad():
+        np.testing.assert_allclose(vox(torch.from_numpy(g["pos_vox"])).numpy(), g["out_vox"], atol=1e-6)
     # what our save() writes has the reference's layout: same keys, same "type"/"params" entries
-    for name, model in (("ref_nerf_small.pt", nerf), ("ref_fourier_small.pt", four)):
+    for name, model in (("ref_nerf_small.pt", nerf), ("ref_fourier_small.pt", four), ("ref_voxels_small.pt", vox)):
         ref_raw = torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=False)
         sd = model.state_dict()
         ours = dict(sd, type=ref_raw["type"], params=model.params)
