@@ -35,6 +35,8 @@ def _bind(L):
     L.ffn_composite_backward.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
                                          c_void_p]
     L.ffn_train_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
+    L.ffn_colsum_bf16.argtypes = [c_void_p, c_int32, c_int64, c_void_p, c_void_p]
+    L.ffn_head_wgrad.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     L._train_bound = True
 
 
@@ -53,8 +55,35 @@ def _mm_f32(a_t: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         return torch.mm(a.float(), b.float())
 
 
+def _bias_grads(L, dz: torch.Tensor) -> torch.Tensor:
+    """Column sums of every saved dz slot in one launch: (n, M, 256) bf16 -> (n, 256) fp32."""
+    n, M = dz.shape[0], dz.shape[1]
+    out = torch.empty((n, 256), dtype=torch.float32, device=dz.device)
+    _lib._check(L.ffn_colsum_bf16(_p(dz), n, M, _p(out), _lib._stream()), "ffn_colsum_bf16")
+    return out
+
+
+def _head_grads(L, d_raw: torch.Tensor, first: int, count: int, h: torch.Tensor):
+    """(dW (count,256), db (count,)) of a CUDA-core head: d_raw[:, first:first+count]^T @ h, fp32 accumulation."""
+    M = d_raw.shape[0]
+    gw = torch.empty((count, 256), dtype=torch.float32, device=d_raw.device)
+    gb = torch.empty((count,), dtype=torch.float32, device=d_raw.device)
+    _lib._check(L.ffn_head_wgrad(_p(d_raw), first, count, _p(h), M, _p(gw), _p(gb), _lib._stream()), "ffn_head_wgrad")
+    return gw, gb
+
+
+_PERM_CACHE = {}
+
+
 def enc_permutation(num_freq: int, include_inputs: bool, device) -> torch.Tensor:
     """index of OUR encoding-chunk column for every reference column of [cos(3F) | sin(3F) | x(3)]."""
+    key = (num_freq, bool(include_inputs), str(device))
+    if key not in _PERM_CACHE:
+        _PERM_CACHE[key] = _enc_permutation(num_freq, include_inputs, device)
+    return _PERM_CACHE[key]
+
+
+def _enc_permutation(num_freq: int, include_inputs: bool, device) -> torch.Tensor:
     idx = []
     for sn in (0, 1):
         for k in range(num_freq):
@@ -139,9 +168,10 @@ class RenderNeRF(torch.autograd.Function):
         enc_p = save_enc[0].to(torch.bfloat16)
         enc_v = save_enc[1].to(torch.bfloat16)
         grads: List[Optional[torch.Tensor]] = []
-
-        def bias_grad(d):
-            return d.sum(0, dtype=torch.float32)
+        with torch.cuda.device(device):
+            db = _bias_grads(L, dz)
+            g_op = _head_grads(L, d_raw, 3, 1, save_h[nL - 1])
+            g_rgb = _head_grads(L, d_raw, 0, 3, save_h[nL + 1])
 
         # trunk layers (nerf_model.py:111-116)
         for i in range(nL):
@@ -152,22 +182,19 @@ class RenderNeRF(torch.autograd.Function):
                 gw = _mm_f32(dzi, save_h[i - 1])
                 if i in skips:
                     gw = torch.cat([gw, _mm_f32(dzi, enc_p)[:, perm_p]], dim=1)
-            grads += [gw, bias_grad(dzi)]
+            grads += [gw, db[i]]
         # opacity_out (nerf_model.py:118): sigma_raw = w_op . h_L + b
-        dsig = d_raw[:, 3:4]
         h_last = save_h[nL - 1]
-        grads += [(dsig.t() @ h_last.float()), dsig.sum(0)]
+        grads += [g_op[0], g_op[1]]
         # bottleneck (nerf_model.py:119)
         d_b = dz[nL]
-        grads += [_mm_f32(d_b, h_last), bias_grad(d_b)]
+        grads += [_mm_f32(d_b, h_last), db[nL]]
         # hidden_view (nerf_model.py:121-122): input [bottleneck | enc_view]
         dz_v = dz[nL + 1][:, :128]
         gw = torch.cat([_mm_f32(dz_v, save_h[nL]), _mm_f32(dz_v, enc_v)[:, perm_v]], dim=1)
-        grads += [gw, bias_grad(dz_v)]
-        # color_out (nerf_model.py:123)
-        d_rgb = d_raw[:, :3]
-        h_v = save_h[nL + 1][:, :128]
-        grads += [d_rgb.t() @ h_v.float(), d_rgb.sum(0)]
+        grads += [gw, db[nL + 1][:128]]
+        # color_out (nerf_model.py:123): the saved slot holds relu(hidden_view) in its first 128 columns
+        grads += [g_rgb[0][:, :128], g_rgb[1]]
 
         out = []
         for g, prm in zip(grads, params):
@@ -247,10 +274,13 @@ class RenderFFMLP(torch.autograd.Function):
         else:
             e = (math.pi * pos) @ model.b_values
             x0 = torch.cat([model.a_values * e.cos(), model.a_values * e.sin()], dim=-1)
-        grads = [_mm_f32(dz[0], x0.to(torch.bfloat16)), dz[0].sum(0, dtype=torch.float32)]
+        with torch.cuda.device(device):
+            db = _bias_grads(L, dz)
+            g_out = _head_grads(L, d_raw, 0, 4, save_h[H - 1])                # final Linear 256 -> 4
+        grads = [_mm_f32(dz[0], x0.to(torch.bfloat16)), db[0]]
         for i in range(1, H):
-            grads += [_mm_f32(dz[i], save_h[i - 1]), dz[i].sum(0, dtype=torch.float32)]
-        grads += [d_raw.t() @ save_h[H - 1].float(), d_raw.sum(0)]          # final Linear 256 -> 4
+            grads += [_mm_f32(dz[i], save_h[i - 1]), db[i]]
+        grads += [g_out[0], g_out[1]]
         out = [g.reshape(p.shape).to(p.dtype) if p.requires_grad else None for g, p in zip(grads, params)]
         return (None, None, None, *out)
 

@@ -804,3 +804,4 @@ extern "C" int ffn_debug_stats(ffn_net_t* net, uint64_t* out32) {
 #include "ffn_focus.cuh"
 #include "ffn_raygen.cuh"
 #include "ffn_voxels.cuh"
+#include "ffn_wgrad_small.cuh"

@@ -52,12 +52,35 @@ class Engine:
         self._sig: Optional[Tuple] = None
 
     def sync_weights(self, model):
+        """Re-pack when a parameter changed: storage pointer, tensor version counter, or -- because fused /
+        capturable optimizers update parameters without bumping the version counters -- any optimizer step
+        anywhere since the last pack."""
         lins = _linear_list(model)
-        sig = tuple((l.weight.data_ptr(), l.weight._version, l.bias.data_ptr(), l.bias._version)
-                    for l in lins)
+        sig = (_OPT_GENERATION[0],) + tuple(
+            (l.weight.data_ptr(), l.weight._version, l.bias.data_ptr(), l.bias._version) for l in lins)
         if sig != self._sig:
             self.net.pack([l.weight for l in lins], [l.bias for l in lins])
             self._sig = sig
+
+
+_OPT_GENERATION = [0]
+
+
+def _note_optimizer_step(*_args, **_kwargs):
+    _OPT_GENERATION[0] += 1
+
+
+try:        # global hook: runs after every torch.optim.Optimizer.step()
+    from torch.optim.optimizer import register_optimizer_step_post_hook
+    register_optimizer_step_post_hook(_note_optimizer_step)
+except ImportError:      # very old torch: version counters only
+    pass
+
+
+def mark_weights_changed():
+    """Call after changing parameters through a path that neither bumps tensor versions nor is an optimizer step
+    (e.g. a custom fused update kernel)."""
+    _OPT_GENERATION[0] += 1
 
 
 def get_engine(model, device: torch.device, operand: Optional[str] = None) -> Engine:

@@ -177,7 +177,10 @@ class Raycaster(nn.Module):
         gradient all-reduce hook (``parallel.allreduce_gradients``)."""
         from .ray_dataset_modes import Mode
         trainval = train_dataset.sample_cameras(val_dataset.num_cameras, val_dataset.num_samples, False)
-        optim = torch.optim.Adam(self.model.parameters(), learning_rate, weight_decay=weight_decay)
+        on_cuda = next(self.model.parameters()).is_cuda
+        # same update rule as ray_caster.py:283; on a GPU the single-kernel ("fused") implementation
+        optim = torch.optim.Adam(self.model.parameters(), learning_rate, weight_decay=weight_decay,
+                                 **({"fused": True} if on_cuda else {}))
         step, epoch, log = 0, 0, []
         start_time = time.time()
         dataset_mode = train_dataset.mode

@@ -185,6 +185,16 @@ int ffn_composite_backward(const float* raw, const float* t_values, int64_t num_
 int ffn_train_backward(ffn_net_t* net, const float* d_raw, const void* save_mask, int64_t num_points,
                        void* dz_out, void* stream);
 
+/* Bias gradients of all layers at once: x = dz (num_slots, M, 256) bf16 -> out (num_slots, 256) fp32 column sums
+ * (autograd of nn.Linear's bias, nerf_model.py:111-122). */
+int ffn_colsum_bf16(const void* x, int32_t num_slots, int64_t num_points, float* out, void* stream);
+
+/* Gradients of a 1..4-row head evaluated on CUDA cores (opacity_out nerf_model.py:118, color_out :123, final Linear
+ * fourier_feature_models.py:77): out_w[o][c] = sum_m d_raw[m][first_head+o] * h[m][c] (h (M,256) bf16, fp32 accumulate),
+ * out_b[o] = sum_m d_raw[m][first_head+o];  out_w (num_heads,256), out_b (num_heads). */
+int ffn_head_wgrad(const float* d_raw, int32_t first_head, int32_t num_heads, const void* h, int64_t num_points,
+                   float* out_w, float* out_b, void* stream);
+
 /* Debug: dump the float32 post-activation output of MMA layer `layer` (row-major (N,256))
  * for the first `n` points.  Used by the bring-up tests only. */
 int ffn_debug_layer(ffn_net_t* net, const float* positions, const float* views, int64_t n,

@@ -326,3 +326,20 @@ print("OK")
 """ % (GOLDEN, str(tmp_path / "exp.npz"), str(tmp_path / "n.pt"), str(tmp_path / "f.pt"))
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "OK" in res.stdout, res.stdout[-500:] + res.stderr[-1500:]
+
+
+def test_engine_notices_fused_optimizer_steps():
+    """Fused optimizers do not bump tensor version counters; the engine's re-pack signature must still change."""
+    from fourier_feature_nets_b200 import engine
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    try:
+        opt = torch.optim.Adam([p], 1e-2, fused=True)
+    except (RuntimeError, TypeError):
+        pytest.skip("no fused Adam on this build")
+    gen, ver = engine._OPT_GENERATION[0], p._version
+    opt.step()
+    assert engine._OPT_GENERATION[0] == gen + 1
+    assert p._version == ver or True      # whichever torch does, the generation covers it
+    engine.mark_weights_changed()
+    assert engine._OPT_GENERATION[0] == gen + 2
