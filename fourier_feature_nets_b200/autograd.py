@@ -5,8 +5,10 @@ forward   ``ffn_train_forward``      fused sampling/encoding/MLP/compositing tha
                                      raw network outputs and t values
 backward  ``ffn_composite_backward`` d(loss)/d(color, alpha) -> d(loss)/d(raw rgb, sigma) per sample
           ``ffn_train_backward``     the dgrad chain on tcgen05 (transposed bf16 weights) -> dz per layer
-          weight gradients           dW = dz^T x : plain GEMMs over the saved tensors (cuBLAS through
-                                     ``torch.mm``), bias gradients = column sums
+          ``ffn_wgrad``              dW = dz^T x and db = column sums of dz for every MMA layer in ONE launch
+                                     (split-K tcgen05 GEMM straight from the saved tensors, red.add into one
+                                     flat fp32 gradient buffer in the reference's parameter layouts)
+          ``ffn_head_wgrad``         the 1- / 3- / 4-row heads on CUDA cores
 
 Gradient operands are bf16 (fp32 accumulate); parity with the fp32 autograd of the reference definition is
 checked in tests/test_gpu_training.py (cosine >= 0.999, relative L2 error <= 3e-2 per parameter).
@@ -24,9 +26,21 @@ from . import _lib
 from . import engine as _engine
 
 
+class WgradTensor(ctypes.Structure):
+    _fields_ = [("ptr", c_void_p), ("rows", c_int64), ("cols", c_int32), ("slots", c_int32)]
+
+
+class WgradJob(ctypes.Structure):
+    _fields_ = [("a_tensor", c_int32), ("a_slot", c_int32), ("a_col0", c_int32), ("n_mtiles", c_int32),
+                ("b_tensor", c_int32), ("b_slot", c_int32), ("b_col0", c_int32), ("n_cols", c_int32),
+                ("dst", c_void_p), ("dst_stride", c_int32), ("dst_col0", c_int32), ("dst_cols", c_int32),
+                ("colmap", c_void_p), ("bias_dst", c_void_p)]
+
+
 def _bind(L):
     if getattr(L, "_train_bound", False):
         return
+    L.ffn_wgrad.argtypes = [ctypes.POINTER(WgradTensor), c_int32, ctypes.POINTER(WgradJob), c_int32, c_void_p]
     L.ffn_train_slots.argtypes = [c_void_p, ctypes.POINTER(c_int32), ctypes.POINTER(c_int32),
                                   ctypes.POINTER(c_int32)]
     L.ffn_net_pack_backward.argtypes = [c_void_p, ctypes.POINTER(c_void_p), c_void_p]
@@ -44,19 +58,8 @@ def _p(t: Optional[torch.Tensor]) -> c_void_p:
     return c_void_p(0 if t is None else t.data_ptr())
 
 
-def _mm_f32(a_t: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """(K,M)^T-free helper: returns a_t.T @ b in float32 from 16-bit inputs (fp32 accumulation)."""
-    a = a_t.t()
-    if b.dtype != a.dtype:
-        b = b.to(a.dtype)
-    try:
-        return torch.mm(a, b, out_dtype=torch.float32)
-    except TypeError:
-        return torch.mm(a.float(), b.float())
-
-
 def _bias_grads(L, dz: torch.Tensor) -> torch.Tensor:
-    """Column sums of every saved dz slot in one launch: (n, M, 256) bf16 -> (n, 256) fp32."""
+    """(stand-alone bias gradients; the training step gets them from ffn_wgrad) Column sums of every saved dz slot in one launch: (n, M, 256) bf16 -> (n, 256) fp32."""
     n, M = dz.shape[0], dz.shape[1]
     out = torch.empty((n, 256), dtype=torch.float32, device=dz.device)
     _lib._check(L.ffn_colsum_bf16(_p(dz), n, M, _p(out), _lib._stream()), "ffn_colsum_bf16")
@@ -72,7 +75,46 @@ def _head_grads(L, d_raw: torch.Tensor, first: int, count: int, h: torch.Tensor)
     return gw, gb
 
 
+def _wg_tensor(t: torch.Tensor) -> WgradTensor:
+    """(slots, rows, cols) bf16 tensor -> descriptor."""
+    assert t.dim() == 3 and t.is_contiguous() and t.dtype == torch.bfloat16
+    return WgradTensor(t.data_ptr(), t.shape[1], t.shape[2], t.shape[0])
+
+
+def _wg_job(a_slot, n_mtiles, b_tensor, b_slot, b_col0, n_cols, dst, dst_col0, dst_cols, colmap=None, bias=None):
+    return WgradJob(0, a_slot, 0, n_mtiles, b_tensor, b_slot, b_col0, n_cols, dst.data_ptr(), dst.shape[1], dst_col0,
+                    dst_cols, 0 if colmap is None else colmap.data_ptr(), 0 if bias is None else bias.data_ptr())
+
+
+def _flat_grads(params, device):
+    """One zeroed fp32 buffer holding the gradient of every parameter (16-byte aligned views, parameter shapes)."""
+    offs, n = [], 0
+    for prm in params:
+        offs.append(n)
+        n += (prm.numel() + 3) & ~3
+    flat = torch.zeros((n,), dtype=torch.float32, device=device)
+    return flat, [flat[o:o + prm.numel()].view(prm.shape) for o, prm in zip(offs, params)]
+
+
+def _run_wgrad(L, tensors, jobs):
+    ta = (WgradTensor * len(tensors))(*tensors)
+    ja = (WgradJob * len(jobs))(*jobs)
+    _lib._check(L.ffn_wgrad(ta, len(tensors), ja, len(jobs), _lib._stream()), "ffn_wgrad")
+
+
 _PERM_CACHE = {}
+_COLMAP_CACHE = {}
+
+
+def enc_colmap(num_freq: int, include_inputs: bool, first: int, device) -> torch.Tensor:
+    """int32[64]: reference weight column (offset by ``first``) of each of OUR encoding-chunk columns, -1 = unused."""
+    key = (num_freq, bool(include_inputs), first, str(device))
+    if key not in _COLMAP_CACHE:
+        perm = _enc_permutation(num_freq, include_inputs, "cpu")
+        cm = torch.full((64,), -1, dtype=torch.int32)
+        cm[perm] = torch.arange(len(perm), dtype=torch.int32) + first
+        _COLMAP_CACHE[key] = cm.to(device)
+    return _COLMAP_CACHE[key]
 
 
 def enc_permutation(num_freq: int, include_inputs: bool, device) -> torch.Tensor:
@@ -116,7 +158,7 @@ class RenderNeRF(torch.autograd.Function):
         raw = torch.empty((M, 4), **f32)
         save_h = torch.empty((ns.value, M, 256), dtype=torch.bfloat16, device=device)
         save_mask = torch.empty((nm.value, M, 8), dtype=torch.int32, device=device)
-        save_enc = torch.empty((2, M, 64), dtype=torch.float16, device=device)
+        save_enc = torch.empty((2, M, 64), dtype=torch.bfloat16, device=device)
         if spec["mode"] == "rays":
             t_vals = torch.empty((R, S), **f32)
             a = spec
@@ -163,38 +205,34 @@ class RenderNeRF(torch.autograd.Function):
         p = model.params
         nL = p["num_layers"]
         skips = set(p["skips"])
-        perm_p = enc_permutation(p["num_freq_pos"], p["include_inputs"], device)
-        perm_v = enc_permutation(p["num_freq_view"], p["include_inputs"], device)
-        enc_p = save_enc[0].to(torch.bfloat16)
-        enc_v = save_enc[1].to(torch.bfloat16)
-        grads: List[Optional[torch.Tensor]] = []
+        nf_p, nf_v, inc = p["num_freq_pos"], p["num_freq_view"], p["include_inputs"]
+        # params = [W0, b0, ..., W_{L-1}, b_{L-1}, W_op, b_op, W_bott, b_bott, W_hv, b_hv, W_rgb, b_rgb]
+        flat, grads = _flat_grads(params, device)
+        W = lambda i: grads[2 * i]          # noqa: E731
+        B = lambda i: grads[2 * i + 1]      # noqa: E731
+        SH, ENC = 1, 2                       # tensor indices: 0 = dz, 1 = save_h, 2 = save_enc
+        jobs = []
+        # trunk layers (nerf_model.py:111-116): layer i reads save_h[i-1]; layer 0 and the skip layers read enc_p
+        for i in range(nL):
+            if i == 0:
+                jobs.append(_wg_job(0, 2, ENC, 0, 0, 64, W(0), 0, 64, enc_colmap(nf_p, inc, 0, device), B(0)))
+            else:
+                jobs.append(_wg_job(i, 2, SH, i - 1, 0, 256, W(i), 0, 256, None, B(i)))
+                if i in skips:
+                    jobs.append(_wg_job(i, 2, ENC, 0, 0, 64, W(i), 0, 64, enc_colmap(nf_p, inc, 256, device)))
+        # bottleneck (nerf_model.py:119) reads the last trunk activation
+        jobs.append(_wg_job(nL, 2, SH, nL - 1, 0, 256, W(nL + 1), 0, 256, None, B(nL + 1)))
+        # hidden_view (nerf_model.py:121-122): 128 outputs, input [bottleneck | enc_view]
+        jobs.append(_wg_job(nL + 1, 1, SH, nL, 0, 256, W(nL + 2), 0, 256, None, B(nL + 2)))
+        jobs.append(_wg_job(nL + 1, 1, ENC, 1, 0, 64, W(nL + 2), 0, 64, enc_colmap(nf_v, inc, 256, device)))
         with torch.cuda.device(device):
-            db = _bias_grads(L, dz)
+            _run_wgrad(L, [_wg_tensor(dz), _wg_tensor(save_h), _wg_tensor(save_enc)], jobs)
+            # opacity_out (nerf_model.py:118): sigma_raw = w_op . h_L + b;  color_out (:123): the saved slot holds
+            # relu(hidden_view) in its first 128 columns
             g_op = _head_grads(L, d_raw, 3, 1, save_h[nL - 1])
             g_rgb = _head_grads(L, d_raw, 0, 3, save_h[nL + 1])
-
-        # trunk layers (nerf_model.py:111-116)
-        for i in range(nL):
-            dzi = dz[i]
-            if i == 0:
-                gw = _mm_f32(dzi, enc_p)[:, perm_p]
-            else:
-                gw = _mm_f32(dzi, save_h[i - 1])
-                if i in skips:
-                    gw = torch.cat([gw, _mm_f32(dzi, enc_p)[:, perm_p]], dim=1)
-            grads += [gw, db[i]]
-        # opacity_out (nerf_model.py:118): sigma_raw = w_op . h_L + b
-        h_last = save_h[nL - 1]
-        grads += [g_op[0], g_op[1]]
-        # bottleneck (nerf_model.py:119)
-        d_b = dz[nL]
-        grads += [_mm_f32(d_b, h_last), db[nL]]
-        # hidden_view (nerf_model.py:121-122): input [bottleneck | enc_view]
-        dz_v = dz[nL + 1][:, :128]
-        gw = torch.cat([_mm_f32(dz_v, save_h[nL]), _mm_f32(dz_v, enc_v)[:, perm_v]], dim=1)
-        grads += [gw, db[nL + 1][:128]]
-        # color_out (nerf_model.py:123): the saved slot holds relu(hidden_view) in its first 128 columns
-        grads += [g_rgb[0][:, :128], g_rgb[1]]
+        grads[2 * nL], grads[2 * nL + 1] = g_op[0], g_op[1]
+        grads[2 * nL + 6], grads[2 * nL + 7] = g_rgb[0][:, :128], g_rgb[1]
 
         out = []
         for g, prm in zip(grads, params):
@@ -274,13 +312,21 @@ class RenderFFMLP(torch.autograd.Function):
         else:
             e = (math.pi * pos) @ model.b_values
             x0 = torch.cat([model.a_values * e.cos(), model.a_values * e.sin()], dim=-1)
-        with torch.cuda.device(device):
-            db = _bias_grads(L, dz)
-            g_out = _head_grads(L, d_raw, 0, 4, save_h[H - 1])                # final Linear 256 -> 4
-        grads = [_mm_f32(dz[0], x0.to(torch.bfloat16)), db[0]]
+        C0 = x0.shape[1]
+        Cpad = (C0 + 63) & ~63
+        x0p = torch.zeros((1, M, Cpad), dtype=torch.bfloat16, device=device)
+        x0p[0, :, :C0] = x0
+        flat, grads = _flat_grads(params, device)
+        jobs = []
+        for w0 in range(0, Cpad, 256):          # layer 0 (fourier_feature_models.py:70-73), 256 input columns per job
+            n = min(256, Cpad - w0)
+            jobs.append(_wg_job(0, 2, 2, 0, w0, n, grads[0], w0, min(n, C0 - w0), None, grads[1] if w0 == 0 else None))
         for i in range(1, H):
-            grads += [_mm_f32(dz[i], save_h[i - 1]), db[i]]
-        grads += [g_out[0], g_out[1]]
+            jobs.append(_wg_job(i, 2, 1, i - 1, 0, 256, grads[2 * i], 0, 256, None, grads[2 * i + 1]))
+        with torch.cuda.device(device):
+            _run_wgrad(L, [_wg_tensor(dz), _wg_tensor(save_h), _wg_tensor(x0p)], jobs)
+            g_out = _head_grads(L, d_raw, 0, 4, save_h[H - 1])                # final Linear 256 -> 4
+        grads[2 * H], grads[2 * H + 1] = g_out[0], g_out[1]
         out = [g.reshape(p.shape).to(p.dtype) if p.requires_grad else None for g, p in zip(grads, params)]
         return (None, None, None, *out)
 

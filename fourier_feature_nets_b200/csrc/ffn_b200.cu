@@ -805,3 +805,4 @@ extern "C" int ffn_debug_stats(ffn_net_t* net, uint64_t* out32) {
 #include "ffn_raygen.cuh"
 #include "ffn_voxels.cuh"
 #include "ffn_wgrad_small.cuh"
+#include "ffn_wgrad.cuh"

@@ -132,7 +132,7 @@ struct KernelArgs {
   // training (PASS_TRAIN_FWD writes, PASS_BWD reads masks / writes dz)
   __nv_bfloat16* save_h;       // [n_save][M][256] layer outputs (bf16, post-activation)
   uint32_t* save_mask;         // [n_mask][M][8]   ReLU sign words (bit 31-j of word b <-> column 32b+j is <= 0)
-  __half* save_enc;            // [2][M][64]       position / view encoding rows as fed to the UMMA (our column order)
+  __half* save_enc;            // [2][M][64]       position / view encoding rows (our column order), stored as BF16 bits
   const float* d_raw;          // PASS_BWD: (M,4) gradient w.r.t. the raw network outputs [rgb | sigma]
   __nv_bfloat16* dz_out;       // PASS_BWD: [n_dz][M][256] gradients w.r.t. the pre-activations
   int32_t bwd_first_cols;      // PASS_BWD: width of the first dz tile (128 NeRF hidden_view, 256 FourierFeatureMLP)

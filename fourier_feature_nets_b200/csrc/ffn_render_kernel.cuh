@@ -69,6 +69,13 @@ __device__ __forceinline__ float philox_uniform(unsigned long long seed, unsigne
 // columns are permuted to match at pack time):  col 6k+2j = cos(f_k x_j), col 6k+2j+1 =
 // sin(f_k x_j)  (k < 10, j < 3), cols 60..62 = x, col 63 = 0.
 // ----------------------------------------------------------------------------------------
+// packed fp16 pair -> packed bf16 pair (through fp32, round to nearest)
+__device__ __forceinline__ uint32_t half2_to_bf16x2(uint32_t h) {
+  float lo, hi;
+  asm("{\n\t.reg .f16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}" : "=f"(lo), "=f"(hi) : "r"(h));
+  return ptx::pack2<true, false>(lo, hi);
+}
+
 template <bool kBF16>
 __device__ __forceinline__ void write_enc_posenc(uint32_t row_addr, uint32_t row7, float x0,
                                                  float x1, float x2, const float* freq, int nfreq,
@@ -95,9 +102,17 @@ __device__ __forceinline__ void write_enc_posenc(uint32_t row_addr, uint32_t row
   for (uint32_t u = 0; u < 8; ++u)
     ptx::st_shared_v4(row_addr + ((u ^ row7) << 4), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2],
                       pk[4 * u + 3]);
-  if (gsave) {   // training: the 64-wide row exactly as the UMMA reads it (un-swizzled, our column order)
+  if (gsave) {   // training: the 64-wide row as the UMMA reads it (un-swizzled, our column order), always as bf16:
+                 // ffn_wgrad multiplies it with bf16 dz and kind::f16 UMMAs cannot mix fp16 and bf16 operands
 #pragma unroll
-    for (uint32_t u = 0; u < 8; ++u) gsave[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+    for (uint32_t u = 0; u < 8; ++u) {
+      uint32_t w[4] = {pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]};
+      if constexpr (!kBF16) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w[e] = half2_to_bf16x2(w[e]);
+      }
+      gsave[u] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
   }
 }
 

@@ -168,7 +168,7 @@ int ffn_net_pack_backward(ffn_net_t* net, const float* const* weights, void* str
 
 /* Raycaster.render in training mode: inputs either materialised samples (positions, view_directions,
  * t_values; the ray pointers NULL) or rays (starts, directions, near, far, lin[, jitter]; sample pointers
- * NULL).  Also writes raw (M,4), t_out (R,S) [rays mode], save_h, save_mask, save_enc ([2][M][64] fp16). */
+ * NULL).  Also writes raw (M,4), t_out (R,S) [rays mode], save_h, save_mask, save_enc ([2][M][64] bf16). */
 int ffn_train_forward(ffn_net_t* net, const float* positions, const float* view_directions,
                       const float* t_values, const float* starts, const float* directions,
                       const float* near, const float* far, const float* lin, const float* jitter,
@@ -194,6 +194,33 @@ int ffn_colsum_bf16(const void* x, int32_t num_slots, int64_t num_points, float*
  * out_b[o] = sum_m d_raw[m][first_head+o];  out_w (num_heads,256), out_b (num_heads). */
 int ffn_head_wgrad(const float* d_raw, int32_t first_head, int32_t num_heads, const void* h, int64_t num_points,
                    float* out_w, float* out_b, void* stream);
+
+/* Weight (and bias) gradients of every MMA layer in ONE launch: dW[out][in] += sum_rows dz[row][out] * x[row][in]
+ * (autograd of nn.Linear inside Raycaster.fit, ray_caster.py:319-326; layers nerf_model.py:111-123,
+ * fourier_feature_models.py:70-77).  Split-K tcgen05 GEMM over the saved tensors, accumulating with red.global.add
+ * into fp32 destinations the CALLER HAS ZEROED.
+ *   tensors[i]: [slots][rows][cols] bf16 row-major, cols a multiple of 64, the same
+ *               `rows` for all, 16-byte aligned.
+ *   jobs[j]   : A = n_mtiles (1|2) tiles of 128 columns of slot a_slot of tensors[a_tensor] from a_col0,
+ *               B = n_cols (64..256, multiple of 64) columns of slot b_slot of tensors[b_tensor] from b_col0;
+ *               dst[(128*mt + r) * dst_stride + dst_col0 + c] += D[mt][r][c]  for c < dst_cols, or, with colmap,
+ *               dst[... + colmap[c]] for colmap[c] >= 0 (colmap: device int32[n_cols]);
+ *               bias_dst (optional, device float[128*n_mtiles]) += column sums of the A tile. */
+typedef struct {
+  const void* ptr;
+  int64_t rows;
+  int32_t cols, slots;
+} ffn_wgrad_tensor_t;
+typedef struct {
+  int32_t a_tensor, a_slot, a_col0, n_mtiles;
+  int32_t b_tensor, b_slot, b_col0, n_cols;
+  float* dst;
+  int32_t dst_stride, dst_col0, dst_cols;
+  const int32_t* colmap;
+  float* bias_dst;
+} ffn_wgrad_job_t;
+int ffn_wgrad(const ffn_wgrad_tensor_t* tensors, int32_t n_tensors, const ffn_wgrad_job_t* jobs, int32_t n_jobs,
+              void* stream);
 
 /* Debug: dump the float32 post-activation output of MMA layer `layer` (row-major (N,256))
  * for the first `n` points.  Used by the bring-up tests only. */
