@@ -10,6 +10,7 @@ from .fourier_feature_models import (BasicFourierMLP, FourierFeatureMLP, Gaussia
                                      PositionalFourierMLP)
 from .image_dataset import ImageDataset, RayDataset
 from .nerf_model import NeRF
+from .optim import ClipAdam
 from .ray_caster import Raycaster
 from .ray_dataset_modes import Mode
 from .ray_sampler import FocusBundle, RayBundle, RaySampler, RaySamples
@@ -27,4 +28,4 @@ __all__ = ["CameraInfo", "Resolution", "MLP", "NeRF", "BasicFourierMLP", "Fourie
            "PositionalFourierMLP", "GaussianFourierMLP", "Raycaster", "RayCaster", "RaySampler",
            "RaySamples", "RayBundle", "FocusBundle", "RenderResult", "Mode", "ImageDataset", "RayDataset", "calculate_blend_weights",
            "exponential_lr_decay", "linspace", "load_model", "orbit", "ETABar", "EvaluationVisualizer",
-           "OrbitVideoVisualizer", "ActivationVisualizer", "ComparisonVisualizer", "Voxels", "__version__"]
+           "OrbitVideoVisualizer", "ActivationVisualizer", "ComparisonVisualizer", "Voxels", "ClipAdam", "__version__"]

@@ -113,7 +113,7 @@ EXPORTED_SYMBOLS = [
     "ffn_render_rays", "ffn_composite", "ffn_blend_weights", "ffn_debug_layer", "ffn_debug_stats", "ffn_launch_count",
     "ffn_focus_t", "ffn_focus_sample", "ffn_render_rays_t", "ffn_generate_rays", "ffn_voxels_forward",
     "ffn_train_slots", "ffn_net_pack_backward", "ffn_train_forward", "ffn_composite_backward",
-    "ffn_train_backward", "ffn_colsum_bf16", "ffn_head_wgrad", "ffn_wgrad",
+    "ffn_train_backward", "ffn_colsum_bf16", "ffn_head_wgrad", "ffn_wgrad", "ffn_clip_adam",
 ]
 
 

@@ -178,9 +178,14 @@ class Raycaster(nn.Module):
         from .ray_dataset_modes import Mode
         trainval = train_dataset.sample_cameras(val_dataset.num_cameras, val_dataset.num_samples, False)
         on_cuda = next(self.model.parameters()).is_cuda
-        # same update rule as ray_caster.py:283; on a GPU the single-kernel ("fused") implementation
-        optim = torch.optim.Adam(self.model.parameters(), learning_rate, weight_decay=weight_decay,
-                                 **({"fused": True} if on_cuda else {}))
+        # same update rule as ray_caster.py:283,327-329; on a GPU both clips and Adam are two launches (optim.ClipAdam)
+        fused_step = on_cuda and self.train_kernels
+        if fused_step:
+            from .optim import ClipAdam
+            optim = ClipAdam(self.model.parameters(), learning_rate, weight_decay=weight_decay, clip_value=0.1,
+                             max_norm=0.1)
+        else:
+            optim = torch.optim.Adam(self.model.parameters(), learning_rate, weight_decay=weight_decay)
         step, epoch, log = 0, 0, []
         start_time = time.time()
         dataset_mode = train_dataset.mode
@@ -207,8 +212,9 @@ class Raycaster(nn.Module):
                 loss.backward()
                 if grad_sync is not None:
                     grad_sync(self.model)
-                torch.nn.utils.clip_grad_value_(self.model.parameters(), 0.1)
-                torch.nn.utils.clip_grad_norm_(self.model.parameters(), 0.1)
+                if not fused_step:
+                    torch.nn.utils.clip_grad_value_(self.model.parameters(), 0.1)
+                    torch.nn.utils.clip_grad_norm_(self.model.parameters(), 0.1)
                 optim.step()
 
                 if step < 10 or step % report_interval == 0:

@@ -222,6 +222,21 @@ typedef struct {
 int ffn_wgrad(const ffn_wgrad_tensor_t* tensors, int32_t n_tensors, const ffn_wgrad_job_t* jobs, int32_t n_jobs,
               void* stream);
 
+/* Optimiser step of Raycaster.fit (ray_caster.py:327-329) in two launches: clip_grad_value_(clip_value) ->
+ * clip_grad_norm_(max_norm) (both written back into grad, <= 0 disables) -> torch.optim.Adam update with L2
+ * weight decay.  bias_correction{1,2} = 1 - beta{1,2}^step.  norm_sq (device float[1]) receives the squared
+ * total norm of the value-clipped gradients.  All tensors fp32, contiguous, on the current device. */
+typedef struct {
+  float* param;
+  float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+} ffn_adam_tensor_t;
+int ffn_clip_adam(const ffn_adam_tensor_t* tensors, int32_t n, float clip_value, float max_norm, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
+                  float bias_correction2, float* norm_sq, void* stream);
+
 /* Debug: dump the float32 post-activation output of MMA layer `layer` (row-major (N,256))
  * for the first `n` points.  Used by the bring-up tests only. */
 int ffn_debug_layer(ffn_net_t* net, const float* positions, const float* views, int64_t n,

@@ -211,3 +211,45 @@ def test_fit_on_device_resident_dataset(tmp_path):
     assert _lib.launch_count() - before > 200          # the kernels did the work
     assert len(log) >= 2 and log[-1].val_psnr > log[0].val_psnr, [e.val_psnr for e in log]
     assert any(f.endswith(".png") for f in os.listdir(os.path.join(str(tmp_path), "val")))
+
+
+@pytest.mark.parametrize("weight_decay", [0.0, 1e-3])
+def test_clip_adam_matches_torch_clips_and_adam(weight_decay):
+    """ffn_clip_adam == clip_grad_value_(0.1) -> clip_grad_norm_(0.1) -> torch.optim.Adam.step() (ray_caster.py:327-329).
+    fp32 both sides; tolerance 2e-6 absolute on parameters of magnitude <= 1 after 6 steps of lr 5e-3 (the two differ by
+    summation order of the norm and fused-multiply-add contraction only)."""
+    torch.manual_seed(1)
+    ref_model = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True).to(DEV)
+    our_model = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True).to(DEV)
+    our_model.load_state_dict(ref_model.state_dict())
+    ref_opt = torch.optim.Adam(ref_model.parameters(), 5e-3, weight_decay=weight_decay)
+    our_opt = ffn.ClipAdam(our_model.parameters(), 5e-3, weight_decay=weight_decay, clip_value=0.1, max_norm=0.1)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    for it in range(6):
+        scale = [3.0, 0.5, 0.02, 1e-4, 0.3, 0.05][it]       # both clips active / only the norm clip / neither
+        for pr, po in zip(ref_model.parameters(), our_model.parameters()):
+            gr = torch.randn(pr.shape, device=DEV, generator=g) * scale
+            pr.grad, po.grad = gr.clone(), gr.clone()
+        before = _lib.launch_count()
+        torch.nn.utils.clip_grad_value_(ref_model.parameters(), 0.1)
+        ref_norm = torch.nn.utils.clip_grad_norm_(ref_model.parameters(), 0.1)
+        ref_opt.step()
+        for group in our_opt.param_groups:
+            group["lr"] = ref_opt.param_groups[0]["lr"]
+        our_opt.step()
+        assert _lib.launch_count() - before == 2
+        assert abs(our_opt.total_norm() - ref_norm.item()) <= 1e-5 * max(1.0, ref_norm.item())
+        for (n, pr), po in zip(ref_model.named_parameters(), our_model.parameters()):
+            assert (pr.grad - po.grad).abs().max().item() <= 1e-6 * max(1.0, pr.grad.abs().max().item()), (it, n)
+            assert (pr - po).abs().max().item() <= 2e-6, (it, n, (pr - po).abs().max().item())
+    # the engine re-packs after ClipAdam.step (global optimizer hook): a render sees the new weights
+    rc = ffn.Raycaster(our_model)
+    bundle = make_batch(64, 32).to(DEV)
+    with torch.no_grad():
+        a = rc.render(bundle, False).color
+        rc.train_kernels = False
+        our_model.train()
+    rc2 = ffn.Raycaster(ref_model)
+    with torch.no_grad():
+        b = rc2.render(bundle, False).color
+    assert (a - b).abs().max().item() <= 2.5e-3

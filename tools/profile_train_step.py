@@ -22,7 +22,7 @@ R, S = args.rays, args.samples
 torch.manual_seed(20080524)
 model = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True).to(dev)
 rc = ffn.Raycaster(model)
-opt = torch.optim.Adam(model.parameters(), 5e-4, fused=args.fused_adam)
+opt = torch.optim.Adam(model.parameters(), 5e-4, fused=True) if args.fused_adam else ffn.ClipAdam(model.parameters(), 5e-4)
 g = torch.Generator(device=dev).manual_seed(0)
 o = torch.tensor([0.0, 0.3, -4.0], device=dev).repeat(R, 1)
 d = torch.nn.functional.normalize(torch.randn((R, 3), device=dev, generator=g) * 0.15
@@ -46,8 +46,9 @@ def step(i, timed=False):
     t = mark("forward", t)
     loss.backward()
     t = mark("backward", t)
-    torch.nn.utils.clip_grad_value_(model.parameters(), 0.1)
-    torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)
+    if args.fused_adam:
+        torch.nn.utils.clip_grad_value_(model.parameters(), 0.1)
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)
     t = mark("clip", t)
     opt.step()
     mark("adam", t)
@@ -73,5 +74,5 @@ rows = [e for e in prof.key_averages() if e.device_time_total > 0]
 rows.sort(key=lambda e: -e.device_time_total)
 tot = sum(e.device_time_total for e in rows)
 print("GPU busy per step: %.3f ms in %d launches" % (tot / args.steps / 1e3, sum(e.count for e in rows) / args.steps))
-for e in rows[:22]:
+for e in rows[:60]:
     print("  %7.1f us  x%-3d %s" % (e.device_time_total / args.steps, e.count // args.steps, e.key[:90]))
