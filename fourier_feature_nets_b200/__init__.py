@@ -11,6 +11,7 @@ from .fourier_feature_models import (BasicFourierMLP, FourierFeatureMLP, Gaussia
 from .image_dataset import ImageDataset, RayDataset
 from .nerf_model import NeRF
 from .optim import ClipAdam
+from .pixel_dataset import PixelData, PixelDataset
 from .ray_caster import Raycaster
 from .ray_dataset_modes import Mode
 from .ray_sampler import FocusBundle, RayBundle, RaySampler, RaySamples
@@ -28,4 +29,4 @@ __all__ = ["CameraInfo", "Resolution", "MLP", "NeRF", "BasicFourierMLP", "Fourie
            "PositionalFourierMLP", "GaussianFourierMLP", "Raycaster", "RayCaster", "RaySampler",
            "RaySamples", "RayBundle", "FocusBundle", "RenderResult", "Mode", "ImageDataset", "RayDataset", "calculate_blend_weights",
            "exponential_lr_decay", "linspace", "load_model", "orbit", "ETABar", "EvaluationVisualizer",
-           "OrbitVideoVisualizer", "ActivationVisualizer", "ComparisonVisualizer", "Voxels", "ClipAdam", "__version__"]
+           "OrbitVideoVisualizer", "ActivationVisualizer", "ComparisonVisualizer", "Voxels", "ClipAdam", "PixelDataset", "PixelData", "__version__"]

@@ -47,11 +47,12 @@ def allreduce_gradients(model: torch.nn.Module, average: bool = True):
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     if average:
         flat /= ws
-    off = 0
+    views, off = [], 0
     for g in grads:
         n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
+        views.append(flat[off:off + n].view_as(g))
         off += n
+    torch._foreach_copy_(grads, views)      # one multi-tensor launch instead of one copy per parameter
 
 
 def broadcast_parameters(model: torch.nn.Module, src: int = 0):

@@ -14,6 +14,11 @@ script = os.path.abspath(sys.argv[1])
 sys.argv = [script] + sys.argv[2:]
 sys.path = [os.path.join(ROOT, "compat"), ROOT] + [p for p in sys.path
                                                      if os.path.abspath(p or ".") != os.path.dirname(script)]
+if not os.environ.get("DISPLAY"):
+    # headless box: train_image_regression.py / train_signal_regression.py preview with cv2.imshow when not on AzureML
+    import cv2
+    cv2.imshow = lambda *a, **k: None
+    cv2.waitKey = lambda *a, **k: -1
 code = compile(open(script).read(), script, "exec")
 globs = {"__name__": "__main__", "__file__": script}
 exec(code, globs)
