@@ -113,7 +113,7 @@ EXPORTED_SYMBOLS = [
     "ffn_render_rays", "ffn_composite", "ffn_blend_weights", "ffn_debug_layer", "ffn_debug_stats", "ffn_launch_count",
     "ffn_focus_t", "ffn_focus_sample", "ffn_render_rays_t", "ffn_generate_rays", "ffn_voxels_forward",
     "ffn_train_slots", "ffn_net_pack_backward", "ffn_train_forward", "ffn_composite_backward",
-    "ffn_train_backward", "ffn_colsum_bf16", "ffn_head_wgrad", "ffn_wgrad", "ffn_clip_adam",
+    "ffn_train_backward", "ffn_colsum_bf16", "ffn_head_wgrad", "ffn_wgrad", "ffn_clip_adam", "ffn_mse_loss",
 ]
 
 
@@ -127,7 +127,29 @@ def launch_count() -> int:
 
 
 def _stream() -> c_void_p:
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    """Raw handle of PyTorch's current stream on the current device (one C call: ``torch.cuda.current_stream()``
+    builds a Python ``Stream`` object and costs ~20 us, nine times per training step)."""
+    return c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+
+
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL_CTX = _NullCtx()
+
+
+def on_device(device):
+    """``torch.cuda.device(device)`` only when it is not already the current device (the context manager costs
+    ~10 us, the check one C call; a training step enters it a dozen times)."""
+    idx = device.index if isinstance(device, torch.device) else int(device)
+    if idx is None or idx == torch._C._cuda_getDevice():
+        return _NULL_CTX
+    return torch.cuda.device(idx)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> c_void_p:
@@ -183,7 +205,7 @@ class Net:
             d.freq_view[i] = float(f)
         d.operand_dtype = operand
         h = c_void_p()
-        with torch.cuda.device(device):
+        with on_device(device):
             _check(lib().ffn_nerf_create(byref(d), byref(h)), "ffn_nerf_create")
         return Net(h, device)
 
@@ -192,7 +214,7 @@ class Net:
               b_values: Optional[torch.Tensor], device: torch.device,
               operand: int = OPERAND_FP16) -> "Net":
         h = c_void_p()
-        with torch.cuda.device(device):
+        with on_device(device):
             if b_values is None:
                 _check(lib().ffn_ffmlp_create(num_hidden, num_channels, 0, None, None, operand, byref(h)),
                        "ffn_ffmlp_create")
@@ -215,7 +237,7 @@ class Net:
         self._keepalive = ws + bs
         wa = (c_void_p * len(ws))(*[w.data_ptr() for w in ws])
         ba = (c_void_p * len(bs))(*[b.data_ptr() for b in bs])
-        with torch.cuda.device(self.device):
+        with on_device(self.device):
             _check(lib().ffn_net_pack(self.handle, wa, ba, _stream()), "ffn_net_pack")
 
     # -- launches ----------------------------------------------------------------------
@@ -224,7 +246,7 @@ class Net:
         v = _f32c(views, "views") if views is not None else None
         n = pos.shape[0]
         out = torch.empty((n, 4), dtype=torch.float32, device=pos.device)
-        with torch.cuda.device(self.device):
+        with on_device(self.device):
             _check(lib().ffn_mlp_forward(self.handle, _ptr(pos), _ptr(v), n, _ptr(out), _stream()),
                    "ffn_mlp_forward")
         return out
@@ -234,7 +256,7 @@ class Net:
         v = _f32c(views, "views") if views is not None else None
         n = pos.shape[0]
         out = torch.zeros((n, 256), dtype=torch.float32, device=pos.device)
-        with torch.cuda.device(self.device):
+        with on_device(self.device):
             _check(lib().ffn_debug_layer(self.handle, _ptr(pos), _ptr(v), n, layer, _ptr(out), _stream()),
                    "ffn_debug_layer")
         return out
@@ -247,7 +269,7 @@ class Net:
         color = torch.empty((R, 3), dtype=torch.float32, device=pos.device)
         alpha = torch.empty((R,), dtype=torch.float32, device=pos.device)
         depth = torch.empty((R,), dtype=torch.float32, device=pos.device) if include_depth else None
-        with torch.cuda.device(self.device):
+        with on_device(self.device):
             _check(lib().ffn_render_samples(self.handle, _ptr(pos), _ptr(v), _ptr(t), R, S, _ptr(color),
                                             _ptr(alpha), _ptr(depth), _ptr(self._nan_flag), _stream()),
                    "ffn_render_samples")
@@ -266,7 +288,7 @@ class Net:
         alpha = torch.empty((R,), dtype=torch.float32, device=o.device)
         depth = torch.empty((R,), dtype=torch.float32, device=o.device) if include_depth else None
         t_out = torch.empty((R, num_samples), dtype=torch.float32, device=o.device) if want_t else None
-        with torch.cuda.device(self.device):
+        with on_device(self.device):
             _check(lib().ffn_render_rays(self.handle, _ptr(o), _ptr(d), _ptr(nr), _ptr(fr), _ptr(ln),
                                          _ptr(j), int(bool(stratified)), c_uint64(seed & (2**64 - 1)),
                                          ray_offset, R, num_samples, _ptr(color), _ptr(alpha),
@@ -285,7 +307,7 @@ class Net:
         uf = _f32c(u_focus, "u_focus") if u_focus is not None else None
         R = o.shape[0]
         t = torch.empty((R, num_samples), dtype=torch.float32, device=o.device)
-        with torch.cuda.device(self.device):
+        with on_device(self.device):
             _check(lib().ffn_focus_sample(self.handle, _ptr(o), _ptr(d), _ptr(nr), _ptr(fr), _ptr(nu), _ptr(fu),
                                           _ptr(lc), _ptr(lu), _ptr(lc), _ptr(ju), _ptr(uf), int(bool(stratified)),
                                           c_uint64(seed & (2**64 - 1)), 0, R, num_samples, _ptr(t), _stream()),
@@ -298,7 +320,7 @@ class Net:
         color = torch.empty((R, 3), dtype=torch.float32, device=o.device)
         alpha = torch.empty((R,), dtype=torch.float32, device=o.device)
         depth = torch.empty((R,), dtype=torch.float32, device=o.device) if include_depth else None
-        with torch.cuda.device(self.device):
+        with on_device(self.device):
             _check(lib().ffn_render_rays_t(self.handle, _ptr(o), _ptr(d), _ptr(t), R, S, _ptr(color), _ptr(alpha),
                                            _ptr(depth), _ptr(self._nan_flag), _stream()), "ffn_render_rays_t")
         return color, alpha, depth
@@ -327,7 +349,7 @@ def composite(raw: torch.Tensor, t_values: torch.Tensor, include_depth: bool = T
     alpha = torch.empty((R,), dtype=torch.float32, device=t.device)
     depth = torch.empty((R,), dtype=torch.float32, device=t.device) if include_depth else None
     weights = torch.empty((R, S), dtype=torch.float32, device=t.device) if want_weights else None
-    with torch.cuda.device(t.device):
+    with on_device(t.device):
         _check(lib().ffn_composite(_ptr(raw), _ptr(t), R, S, _ptr(color), _ptr(alpha), _ptr(depth),
                                    _ptr(weights), _ptr(nan_flag), _stream()), "ffn_composite")
     return color, alpha, depth, weights
@@ -339,7 +361,7 @@ def blend_weights(t_values: torch.Tensor, opacity: torch.Tensor) -> torch.Tensor
     sg = _f32c(opacity, "opacity")
     R, S = t.shape
     w = torch.empty((R, S), dtype=torch.float32, device=t.device)
-    with torch.cuda.device(t.device):
+    with on_device(t.device):
         _check(lib().ffn_blend_weights(_ptr(t), _ptr(sg), R, S, _ptr(w), _stream()), "ffn_blend_weights")
     return w
 
@@ -358,7 +380,7 @@ def generate_rays(unproj: torch.Tensor, cam_pos: torch.Tensor, bounds_min, bound
     valid = torch.empty((n,), dtype=torch.uint8, device=dev)
     lo = (ctypes.c_float * 3)(*[float(v) for v in bounds_min])
     hi = (ctypes.c_float * 3)(*[float(v) for v in bounds_max])
-    with torch.cuda.device(dev):
+    with on_device(dev):
         _check(lib().ffn_generate_rays(_ptr(u), _ptr(pos), lo, hi, C, width, height, _ptr(starts), _ptr(directions),
                                        _ptr(near_far), _ptr(valid), _stream()), "ffn_generate_rays")
     return starts, directions, near_far, valid.bool()
@@ -371,7 +393,7 @@ def voxels_forward(grid_channels_last: torch.Tensor, bias4, scale: float, positi
     n = p.shape[0]
     out = torch.empty((n, 4), dtype=torch.float32, device=p.device)
     b = (ctypes.c_float * 4)(*[float(v) for v in bias4])
-    with torch.cuda.device(p.device):
+    with on_device(p.device):
         _check(lib().ffn_voxels_forward(_ptr(g), b, g.shape[0], float(scale), _ptr(p), n, _ptr(out), _stream()),
                "ffn_voxels_forward")
     return out
@@ -386,7 +408,7 @@ def focus_t(raw_sigma: torch.Tensor, near, far, near_u, far_u, lin_c, lin_u, jit
     t = torch.empty((R, num_samples), dtype=torch.float32, device=raw.device)
     ju = _f32c(jitter_u, "jitter_u") if jitter_u is not None else None
     uf = _f32c(u_focus, "u_focus") if u_focus is not None else None
-    with torch.cuda.device(raw.device):
+    with on_device(raw.device):
         _check(lib().ffn_focus_t(_ptr(raw), stride, _ptr(_f32c(near, "near")), _ptr(_f32c(far, "far")),
                                  _ptr(_f32c(near_u, "near_u")), _ptr(_f32c(far_u, "far_u")), _ptr(_f32c(lin_c, "lin_c")),
                                  _ptr(_f32c(lin_u, "lin_u")), _ptr(_f32c(lin_c, "lin_c")), _ptr(ju), _ptr(uf),

@@ -41,6 +41,7 @@ def _bind(L):
     if getattr(L, "_train_bound", False):
         return
     L.ffn_wgrad.argtypes = [ctypes.POINTER(WgradTensor), c_int32, ctypes.POINTER(WgradJob), c_int32, c_void_p]
+    L.ffn_mse_loss.argtypes = [c_void_p] * 5 + [c_int64, ctypes.c_float] + [c_void_p] * 4
     L.ffn_train_slots.argtypes = [c_void_p, ctypes.POINTER(c_int32), ctypes.POINTER(c_int32),
                                   ctypes.POINTER(c_int32)]
     L.ffn_net_pack_backward.argtypes = [c_void_p, ctypes.POINTER(c_void_p), c_void_p]
@@ -86,14 +87,31 @@ def _wg_job(a_slot, n_mtiles, b_tensor, b_slot, b_col0, n_cols, dst, dst_col0, d
                     dst_cols, 0 if colmap is None else colmap.data_ptr(), 0 if bias is None else bias.data_ptr())
 
 
+_FLAT_LAYOUT = {}
+
+
 def _flat_grads(params, device):
     """One zeroed fp32 buffer holding the gradient of every parameter (16-byte aligned views, parameter shapes)."""
-    offs, n = [], 0
-    for prm in params:
-        offs.append(n)
-        n += (prm.numel() + 3) & ~3
-    flat = torch.zeros((n,), dtype=torch.float32, device=device)
-    return flat, [flat[o:o + prm.numel()].view(prm.shape) for o, prm in zip(offs, params)]
+    key = tuple(tuple(prm.shape) for prm in params)
+    lay = _FLAT_LAYOUT.get(key)
+    if lay is None:
+        sizes = [(math.prod(shape) + 3) & ~3 for shape in key]
+        lay = _FLAT_LAYOUT[key] = (sizes, sum(sizes))
+    sizes, total = lay
+    flat = torch.zeros((total,), dtype=torch.float32, device=device)
+    return flat, [chunk[:math.prod(shape)].view(shape) for chunk, shape in zip(flat.split(sizes), key)]
+
+
+def _as_param_grads(grads, params):
+    out = []
+    for g, prm in zip(grads, params):
+        if not prm.requires_grad:
+            out.append(None)
+        elif g.shape == prm.shape and g.dtype == prm.dtype:
+            out.append(g)
+        else:
+            out.append(g.reshape(prm.shape).to(prm.dtype))
+    return out
 
 
 def _run_wgrad(L, tensors, jobs):
@@ -169,7 +187,7 @@ class RenderNeRF(torch.autograd.Function):
             args = [spec["positions"], spec["view_directions"], spec["t_values"], None, None, None, None, None, None]
             strat, seed = 0, 0
         keep = [t for t in args if t is not None]
-        with torch.cuda.device(device):
+        with _lib.on_device(device):
             _lib._check(L.ffn_train_forward(
                 net.handle, *[_p(t) for t in args], strat, c_uint64(seed & (2 ** 64 - 1)), 0, R, S,
                 _p(color), _p(alpha), _p(depth), _p(raw), _p(t_vals if spec["mode"] == "rays" else None),
@@ -195,7 +213,7 @@ class RenderNeRF(torch.autograd.Function):
         dz = torch.empty((ctx.n_dz, M, 256), dtype=torch.bfloat16, device=device)
         lins = _engine._linear_list(model)
         wptr = (c_void_p * len(lins))(*[l.weight.data_ptr() for l in lins])
-        with torch.cuda.device(device):
+        with _lib.on_device(device):
             _lib._check(L.ffn_composite_backward(_p(raw), _p(t_vals), R, S, _p(gc), _p(ga), _p(d_raw),
                                                  _lib._stream()), "ffn_composite_backward")
             _lib._check(L.ffn_net_pack_backward(net.handle, wptr, _lib._stream()), "ffn_net_pack_backward")
@@ -225,7 +243,7 @@ class RenderNeRF(torch.autograd.Function):
         # hidden_view (nerf_model.py:121-122): 128 outputs, input [bottleneck | enc_view]
         jobs.append(_wg_job(nL + 1, 1, SH, nL, 0, 256, W(nL + 2), 0, 256, None, B(nL + 2)))
         jobs.append(_wg_job(nL + 1, 1, ENC, 1, 0, 64, W(nL + 2), 0, 64, enc_colmap(nf_v, inc, 256, device)))
-        with torch.cuda.device(device):
+        with _lib.on_device(device):
             _run_wgrad(L, [_wg_tensor(dz), _wg_tensor(save_h), _wg_tensor(save_enc)], jobs)
             # opacity_out (nerf_model.py:118): sigma_raw = w_op . h_L + b;  color_out (:123): the saved slot holds
             # relu(hidden_view) in its first 128 columns
@@ -234,10 +252,7 @@ class RenderNeRF(torch.autograd.Function):
         grads[2 * nL], grads[2 * nL + 1] = g_op[0], g_op[1]
         grads[2 * nL + 6], grads[2 * nL + 7] = g_rgb[0][:, :128], g_rgb[1]
 
-        out = []
-        for g, prm in zip(grads, params):
-            out.append(g.reshape(prm.shape).to(prm.dtype) if prm.requires_grad else None)
-        return (None, None, None, *out)
+        return (None, None, None, *_as_param_grads(grads, params))
 
 
 def _positions_from_spec(spec, t_vals):
@@ -275,7 +290,7 @@ class RenderFFMLP(torch.autograd.Function):
             t_vals = spec["t_values"]
             args = [spec["positions"], None, spec["t_values"], None, None, None, None, None, None]
             strat, seed = 0, 0
-        with torch.cuda.device(device):
+        with _lib.on_device(device):
             _lib._check(L.ffn_train_forward(
                 net.handle, *[_p(t) for t in args], strat, c_uint64(seed & (2 ** 64 - 1)), 0, R, S,
                 _p(color), _p(alpha), _p(depth), _p(raw), _p(t_vals if spec["mode"] == "rays" else None),
@@ -298,7 +313,7 @@ class RenderFFMLP(torch.autograd.Function):
         dz = torch.empty((ctx.n_dz, M, 256), dtype=torch.bfloat16, device=device)
         lins = _engine._linear_list(model)
         wptr = (c_void_p * len(lins))(*[l.weight.data_ptr() for l in lins])
-        with torch.cuda.device(device):
+        with _lib.on_device(device):
             _lib._check(L.ffn_composite_backward(_p(raw), _p(t_vals), R, S, _p(gc), _p(ga), _p(d_raw), _lib._stream()),
                         "ffn_composite_backward")
             _lib._check(L.ffn_net_pack_backward(net.handle, wptr, _lib._stream()), "ffn_net_pack_backward")
@@ -323,12 +338,39 @@ class RenderFFMLP(torch.autograd.Function):
             jobs.append(_wg_job(0, 2, 2, 0, w0, n, grads[0], w0, min(n, C0 - w0), None, grads[1] if w0 == 0 else None))
         for i in range(1, H):
             jobs.append(_wg_job(i, 2, 1, i - 1, 0, 256, grads[2 * i], 0, 256, None, grads[2 * i + 1]))
-        with torch.cuda.device(device):
+        with _lib.on_device(device):
             _run_wgrad(L, [_wg_tensor(dz), _wg_tensor(save_h), _wg_tensor(x0p)], jobs)
             g_out = _head_grads(L, d_raw, 0, 4, save_h[H - 1])                # final Linear 256 -> 4
         grads[2 * H], grads[2 * H + 1] = g_out[0], g_out[1]
-        out = [g.reshape(p.shape).to(p.dtype) if p.requires_grad else None for g, p in zip(grads, params)]
-        return (None, None, None, *out)
+        return (None, None, None, *_as_param_grads(grads, params))
+
+
+class MSELoss(torch.autograd.Function):
+    """loss = mean((colors[rays] - color)^2) + alpha_weight * mean((alphas[rays] - alpha)^2) with the ground-truth
+    colour zeroed where the ground-truth alpha is 0 (ImageDataset.render/.loss, image_dataset.py:224-262): value and
+    gradient in ONE launch (``ffn_mse_loss``) instead of ~10 forward and ~12 backward element-wise launches."""
+
+    @staticmethod
+    def forward(ctx, color, alpha, gt_colors, gt_alphas, rays, alpha_weight):
+        L = _lib.lib()
+        _bind(L)
+        R = color.shape[0]
+        color = _lib._f32c(color, "color")
+        alpha = None if gt_alphas is None else _lib._f32c(alpha, "alpha")
+        out = torch.empty((1 + 4 * R,), dtype=torch.float32, device=color.device)
+        loss, g_color, g_alpha = out[0], out[1:1 + 3 * R].view(R, 3), out[1 + 3 * R:]
+        with _lib.on_device(color.device):
+            _lib._check(L.ffn_mse_loss(_p(color), _p(alpha), _p(gt_colors), _p(gt_alphas), _p(rays), R,
+                                       float(alpha_weight), _p(out), c_void_p(g_color.data_ptr()),
+                                       c_void_p(g_alpha.data_ptr()), _lib._stream()), "ffn_mse_loss")
+        ctx.save_for_backward(g_color, g_alpha)
+        ctx.has_alpha = gt_alphas is not None
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        g_color, g_alpha = ctx.saved_tensors
+        return g_color * grad_out, (g_alpha * grad_out if ctx.has_alpha else None), None, None, None, None
 
 
 def render_nerf_train(model, ray_samples, include_depth: bool, lin_fn):

@@ -93,6 +93,11 @@ class ImageDataset(torch.utils.data.Dataset, RayDataset):
             self.alphas = None
             self.alpha_weight = 0
         self.colors = torch.cat(colors)
+        self.fused_loss = True          # False: always the element-wise PyTorch definition of ``loss``
+        # host copies of the index tables: a batch given as a Python list is remapped and filtered on the host,
+        # so a training step needs one small host->device copy and no device->host synchronisation
+        self._host_tables = {Mode.Center: self.crop_index.numpy(), Mode.Sparse: self.sparse_index.numpy(),
+                             Mode.Dilate: self.dilate_index.numpy()}
 
     # ---- device residency ---------------------------------------------------------------
     def to(self, device) -> "ImageDataset":
@@ -148,7 +153,15 @@ class ImageDataset(torch.utils.data.Dataset, RayDataset):
         return RenderResult(color, alpha, None)
 
     def loss(self, _: int, rays: RaySamples, render: RenderResult) -> torch.Tensor:
-        """MSE(colour) + alpha_weight * MSE(alpha)   (image_dataset.py:224-242)."""
+        """MSE(colour) + alpha_weight * MSE(alpha)   (image_dataset.py:224-242).  With predictions and ground truth in
+        HBM this is one launch (value + gradient, ``autograd.MSELoss``); otherwise the PyTorch ops of the reference."""
+        pred = render.color
+        if (self.fused_loss and pred.is_cuda and pred.dtype == torch.float32 and self.colors.device == pred.device
+                and rays.rays.device == pred.device and rays.rays.dtype == torch.int64 and len(pred) > 0):
+            from .autograd import MSELoss
+            use_alpha = self.alphas is not None and self.mode != Mode.Dilate
+            return MSELoss.apply(pred, render.alpha if use_alpha else None, self.colors,
+                                 self.alphas if use_alpha else None, rays.rays.contiguous(), self.alpha_weight)
         actual = self.render(rays).to(render.device)
         color_loss = (actual.color - render.color).square().mean()
         if self.alpha_weight > 0 and actual.alpha is not None:
@@ -162,7 +175,16 @@ class ImageDataset(torch.utils.data.Dataset, RayDataset):
     def get_rays(self, idx: Union[List[int], torch.Tensor], step: int = None) -> RaySamples:
         """Samples of the selected rays (mode remap -> optional pixel subsample -> valid filter)."""
         if not torch.is_tensor(idx):
-            idx = torch.as_tensor(np.asarray(idx).reshape(-1), dtype=torch.long)
+            # host path (the batch lists of Raycaster.fit / _validate): numpy on host copies of the tables
+            idx = np.asarray(idx, dtype=np.int64).reshape(-1)
+            table = self._host_tables.get(self.mode)
+            if table is not None:
+                idx = table[idx]
+            if self.subsample_index:
+                keep = np.fromiter(self.subsample_index, dtype=np.int64)
+                idx = idx[np.isin(idx % self.sampler.rays_per_camera, keep)]
+            idx = idx[self.sampler.valid_mask_host()[idx]]
+            return self.sampler.sample(torch.from_numpy(idx), step)
         table = self._mode_index()
         if table is not None:
             idx = table[idx.to(table.device)]

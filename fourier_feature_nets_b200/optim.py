@@ -38,6 +38,8 @@ class ClipAdam(torch.optim.Optimizer):
         if len(self.param_groups) != 1:
             raise ValueError("ClipAdam clips the norm over ONE parameter group (as Raycaster.fit uses it)")
         self._norm_sq = None
+        self._key = None
+        self._arr = None
 
     def total_norm(self) -> float:
         """Norm of the value-clipped gradients of the last step (one device->host read)."""
@@ -52,34 +54,39 @@ class ClipAdam(torch.optim.Optimizer):
         L = _lib.lib()
         _bind(L)
         group = self.param_groups[0]
-        entries = []
-        device = None
-        step = 0
-        for p in group["params"]:
-            if p.grad is None:
-                continue
-            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
-                raise _lib.FFNError("ClipAdam needs contiguous float32 CUDA parameters")
-            if p.grad.dtype != torch.float32 or not p.grad.is_contiguous():
-                p.grad = p.grad.float().contiguous()
-            state = self.state[p]
-            if not state:
-                state["step"] = 0
-                state["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-            state["step"] += 1
-            step = state["step"]
-            device = p.device
-            entries.append(AdamTensor(p.data_ptr(), p.grad.data_ptr(), state["exp_avg"].data_ptr(),
-                                      state["exp_avg_sq"].data_ptr(), p.numel()))
-        if not entries:
+        params = [p for p in group["params"] if p.grad is not None]
+        if not params:
             return loss
+        device = params[0].device
+        key = tuple(id(p) for p in params)
+        if self._key != key:            # (re)build the descriptor table; afterwards only the grad pointers move
+            for p in params:
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise _lib.FFNError("ClipAdam needs contiguous float32 CUDA parameters")
+                state = self.state[p]
+                if not state:
+                    state["step"] = 0
+                    state["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            self._arr = (AdamTensor * len(params))(*[
+                AdamTensor(p.data_ptr(), 0, self.state[p]["exp_avg"].data_ptr(), self.state[p]["exp_avg_sq"].data_ptr(),
+                           p.numel()) for p in params])
+            self._key = key
+        arr = self._arr
+        step = self.state[params[0]]["step"] + 1
+        for i, p in enumerate(params):
+            g = p.grad
+            if g.dtype != torch.float32 or not g.is_contiguous():
+                p.grad = g = g.float().contiguous()
+            st = self.state[p]
+            arr[i].param, arr[i].grad = p.data_ptr(), g.data_ptr()
+            arr[i].exp_avg, arr[i].exp_avg_sq = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+            st["step"] = step
         if self._norm_sq is None or self._norm_sq.device != device:
             self._norm_sq = torch.zeros((1,), dtype=torch.float32, device=device)
         beta1, beta2 = group["betas"]
-        arr = (AdamTensor * len(entries))(*entries)
-        with torch.cuda.device(device):
-            _lib._check(L.ffn_clip_adam(arr, len(entries), group["clip_value"], group["max_norm"], group["lr"], beta1,
+        with _lib.on_device(device):
+            _lib._check(L.ffn_clip_adam(arr, len(params), group["clip_value"], group["max_norm"], group["lr"], beta1,
                                         beta2, group["eps"], group["weight_decay"], 1.0 - beta1 ** step,
                                         1.0 - beta2 ** step, self._norm_sq.data_ptr(), _lib._stream()), "ffn_clip_adam")
         return loss

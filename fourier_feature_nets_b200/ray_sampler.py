@@ -336,6 +336,12 @@ class RaySampler:
     def rays_for_camera(self, camera: int) -> RaySamples:
         return self.sample(self._valid_for_camera(camera), None)
 
+    def valid_mask_host(self) -> np.ndarray:
+        """Boolean numpy copy of ``valid_mask`` (cached; the mask never changes after construction)."""
+        if getattr(self, "_valid_np", None) is None:
+            self._valid_np = self.valid_mask.cpu().numpy()
+        return self._valid_np
+
     def to_valid(self, idx: Union[List[int], torch.Tensor]) -> Union[List[int], torch.Tensor]:
         """Keep the rays that intersect the volume (order preserved)."""
         if isinstance(idx, torch.Tensor):

@@ -237,6 +237,14 @@ int ffn_clip_adam(const ffn_adam_tensor_t* tensors, int32_t n, float clip_value,
                   float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
                   float bias_correction2, float* norm_sq, void* stream);
 
+/* Loss of Raycaster.fit and its gradient in one launch (ImageDataset.render/.loss, image_dataset.py:224-262):
+ * loss = mean((colors[rays] - color)^2) + alpha_weight * mean((alphas[rays] - alpha)^2), ground-truth colour zeroed
+ * where the ground-truth alpha is 0; gt_alphas == NULL drops the alpha term (and the zeroing).  rays: int64 indices
+ * into the ground-truth tables.  loss: device float[1]; grad_color (R,3), grad_alpha (R) = d loss / d prediction. */
+int ffn_mse_loss(const float* color, const float* alpha, const float* gt_colors, const float* gt_alphas,
+                 const int64_t* rays, int64_t num_rays, float alpha_weight, float* loss, float* grad_color,
+                 float* grad_alpha, void* stream);
+
 /* Debug: dump the float32 post-activation output of MMA layer `layer` (row-major (N,256))
  * for the first `n` points.  Used by the bring-up tests only. */
 int ffn_debug_layer(ffn_net_t* net, const float* positions, const float* views, int64_t n,

@@ -241,7 +241,11 @@ def test_clip_adam_matches_torch_clips_and_adam(weight_decay):
         assert abs(our_opt.total_norm() - ref_norm.item()) <= 1e-5 * max(1.0, ref_norm.item())
         for (n, pr), po in zip(ref_model.named_parameters(), our_model.parameters()):
             assert (pr.grad - po.grad).abs().max().item() <= 1e-6 * max(1.0, pr.grad.abs().max().item()), (it, n)
-            assert (pr - po).abs().max().item() <= 2e-6, (it, n, (pr - po).abs().max().item())
+            # with weight decay g + wd*p cancels to ~eps (1e-8) for a few dozen of the 596k elements; there the update
+            # lr*m/(sqrt(v)+eps) amplifies a 1-ulp difference of g by lr/eps, so the bar is on all but 1e-4 of them
+            diff = (pr - po).abs().flatten()
+            assert diff.max().item() <= (2e-6 if weight_decay == 0 else 5e-4), (it, n, diff.max().item())
+            assert (diff > 2e-6).float().mean().item() <= 1e-4, (it, n)
     # the engine re-packs after ClipAdam.step (global optimizer hook): a render sees the new weights
     rc = ffn.Raycaster(our_model)
     bundle = make_batch(64, 32).to(DEV)
@@ -253,3 +257,38 @@ def test_clip_adam_matches_torch_clips_and_adam(weight_decay):
     with torch.no_grad():
         b = rc2.render(bundle, False).color
     assert (a - b).abs().max().item() <= 2.5e-3
+
+
+@pytest.mark.parametrize("use_alpha", [True, False])
+@pytest.mark.parametrize("R", [1, 1000, 4097])
+def test_fused_mse_loss_matches_the_elementwise_definition(R, use_alpha):
+    """ffn_mse_loss vs the PyTorch ops of ImageDataset.render/.loss (image_dataset.py:224-262): value within 1e-6
+    relative (summation order), gradients within 1e-7 absolute (same fp32 formula)."""
+    from fourier_feature_nets_b200.autograd import MSELoss
+    g = torch.Generator(device=DEV).manual_seed(R)
+    N = 5000
+    gt_c = torch.rand((N, 3), device=DEV, generator=g)
+    gt_a = (torch.rand((N,), device=DEV, generator=g) > 0.4).float() * torch.rand((N,), device=DEV, generator=g)
+    rays = torch.randint(0, N, (R,), device=DEV, generator=g)
+    color = torch.rand((R, 3), device=DEV, generator=g, requires_grad=True)
+    alpha = torch.rand((R,), device=DEV, generator=g, requires_grad=True)
+    c = gt_c[rays]
+    if use_alpha:
+        a = gt_a[rays]
+        c = torch.where(a.unsqueeze(1) > 0, c, torch.zeros_like(c))
+        ref = (c - color).square().mean() + 0.1 * (a - alpha).square().mean()
+    else:
+        ref = (c - color).square().mean()
+    (ref * 1.7).backward()
+    ref_gc, ref_ga = color.grad.clone(), (alpha.grad.clone() if use_alpha else None)
+    color.grad = alpha.grad = None
+    before = _lib.launch_count()
+    out = MSELoss.apply(color, alpha if use_alpha else None, gt_c, gt_a if use_alpha else None, rays, 0.1)
+    assert _lib.launch_count() == before + 1 and out.dim() == 0
+    (out * 1.7).backward()
+    assert abs(out.item() - ref.item()) <= 1e-6 * max(1.0, abs(ref.item()))
+    assert (color.grad - ref_gc).abs().max().item() <= 1e-7
+    if use_alpha:
+        assert (alpha.grad - ref_ga).abs().max().item() <= 1e-7
+    else:
+        assert alpha.grad is None
