@@ -13,6 +13,7 @@ from .nerf_model import NeRF
 from .optim import ClipAdam
 from .pixel_dataset import PixelData, PixelDataset
 from .ray_caster import Raycaster
+from .trainer import FusedTrainer
 from .ray_dataset_modes import Mode
 from .ray_sampler import FocusBundle, RayBundle, RaySampler, RaySamples
 from .utils import (ETABar, RenderResult, calculate_blend_weights, exponential_lr_decay, linspace,
@@ -29,4 +30,4 @@ __all__ = ["CameraInfo", "Resolution", "MLP", "NeRF", "BasicFourierMLP", "Fourie
            "PositionalFourierMLP", "GaussianFourierMLP", "Raycaster", "RayCaster", "RaySampler",
            "RaySamples", "RayBundle", "FocusBundle", "RenderResult", "Mode", "ImageDataset", "RayDataset", "calculate_blend_weights",
            "exponential_lr_decay", "linspace", "load_model", "orbit", "ETABar", "EvaluationVisualizer",
-           "OrbitVideoVisualizer", "ActivationVisualizer", "ComparisonVisualizer", "Voxels", "ClipAdam", "PixelDataset", "PixelData", "__version__"]
+           "OrbitVideoVisualizer", "ActivationVisualizer", "ComparisonVisualizer", "Voxels", "ClipAdam", "FusedTrainer", "PixelDataset", "PixelData", "__version__"]

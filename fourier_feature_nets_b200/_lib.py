@@ -114,6 +114,8 @@ EXPORTED_SYMBOLS = [
     "ffn_focus_t", "ffn_focus_sample", "ffn_render_rays_t", "ffn_generate_rays", "ffn_voxels_forward",
     "ffn_train_slots", "ffn_net_pack_backward", "ffn_train_forward", "ffn_composite_backward",
     "ffn_train_backward", "ffn_colsum_bf16", "ffn_head_wgrad", "ffn_wgrad", "ffn_clip_adam", "ffn_mse_loss",
+    "ffn_trainer_create", "ffn_trainer_destroy", "ffn_trainer_workspace_bytes", "ffn_trainer_backward",
+    "ffn_trainer_update",
 ]
 
 

@@ -51,7 +51,7 @@ def _bind(L):
                                          c_void_p]
     L.ffn_train_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
     L.ffn_colsum_bf16.argtypes = [c_void_p, c_int32, c_int64, c_void_p, c_void_p]
-    L.ffn_head_wgrad.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
+    L.ffn_head_wgrad.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p]
     L._train_bound = True
 
 
@@ -67,13 +67,12 @@ def _bias_grads(L, dz: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def _head_grads(L, d_raw: torch.Tensor, first: int, count: int, h: torch.Tensor):
-    """(dW (count,256), db (count,)) of a CUDA-core head: d_raw[:, first:first+count]^T @ h, fp32 accumulation."""
+def _head_grads(L, d_raw: torch.Tensor, first: int, count: int, h: torch.Tensor, gw: torch.Tensor, gb: torch.Tensor):
+    """Gradients of a CUDA-core head into gw (count, cols <= 256), gb (count,):
+    gw = d_raw[:, first:first+count]^T @ h[:, :cols], fp32 accumulation."""
     M = d_raw.shape[0]
-    gw = torch.empty((count, 256), dtype=torch.float32, device=d_raw.device)
-    gb = torch.empty((count,), dtype=torch.float32, device=d_raw.device)
-    _lib._check(L.ffn_head_wgrad(_p(d_raw), first, count, _p(h), M, _p(gw), _p(gb), _lib._stream()), "ffn_head_wgrad")
-    return gw, gb
+    _lib._check(L.ffn_head_wgrad(_p(d_raw), first, count, _p(h), M, _p(gw), _p(gb), gw.shape[1], _lib._stream()),
+                "ffn_head_wgrad")
 
 
 def _wg_tensor(t: torch.Tensor) -> WgradTensor:
@@ -247,10 +246,9 @@ class RenderNeRF(torch.autograd.Function):
             _run_wgrad(L, [_wg_tensor(dz), _wg_tensor(save_h), _wg_tensor(save_enc)], jobs)
             # opacity_out (nerf_model.py:118): sigma_raw = w_op . h_L + b;  color_out (:123): the saved slot holds
             # relu(hidden_view) in its first 128 columns
-            g_op = _head_grads(L, d_raw, 3, 1, save_h[nL - 1])
-            g_rgb = _head_grads(L, d_raw, 0, 3, save_h[nL + 1])
-        grads[2 * nL], grads[2 * nL + 1] = g_op[0], g_op[1]
-        grads[2 * nL + 6], grads[2 * nL + 7] = g_rgb[0][:, :128], g_rgb[1]
+            _head_grads(L, d_raw, 3, 1, save_h[nL - 1], grads[2 * nL], grads[2 * nL + 1])
+            _head_grads(L, d_raw, 0, 3, save_h[nL + 1], grads[2 * nL + 6], grads[2 * nL + 7])
+        model.__dict__["_ffn_flat_grad"] = flat      # every gradient is a view of it (parallel.allreduce_gradients)
 
         return (None, None, None, *_as_param_grads(grads, params))
 
@@ -340,8 +338,8 @@ class RenderFFMLP(torch.autograd.Function):
             jobs.append(_wg_job(i, 2, 1, i - 1, 0, 256, grads[2 * i], 0, 256, None, grads[2 * i + 1]))
         with _lib.on_device(device):
             _run_wgrad(L, [_wg_tensor(dz), _wg_tensor(save_h), _wg_tensor(x0p)], jobs)
-            g_out = _head_grads(L, d_raw, 0, 4, save_h[H - 1])                # final Linear 256 -> 4
-        grads[2 * H], grads[2 * H + 1] = g_out[0], g_out[1]
+            _head_grads(L, d_raw, 0, 4, save_h[H - 1], grads[2 * H], grads[2 * H + 1])    # final Linear 256 -> 4
+        model.__dict__["_ffn_flat_grad"] = flat
         return (None, None, None, *_as_param_grads(grads, params))
 
 

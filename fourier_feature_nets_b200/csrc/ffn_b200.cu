@@ -808,3 +808,4 @@ extern "C" int ffn_debug_stats(ffn_net_t* net, uint64_t* out32) {
 #include "ffn_wgrad.cuh"
 #include "ffn_optim.cuh"
 #include "ffn_loss.cuh"
+#include "ffn_trainer.cuh"

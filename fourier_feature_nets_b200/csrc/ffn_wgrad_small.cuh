@@ -25,7 +25,8 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& v, float (&f)[8]) {
 template <int kHeads>
 __global__ void __launch_bounds__(kRedThreads)
 rows_reduce_kernel(const __nv_bfloat16* __restrict__ x, long long M, long long slot_stride, const float* __restrict__ d,
-                   int o0, float* __restrict__ out, int out_slot_stride, float* __restrict__ dsum) {
+                   int o0, float* __restrict__ out, int out_slot_stride, float* __restrict__ dsum, int out_row_stride,
+                   int ncols) {
   constexpr int kAcc = kHeads == 0 ? 1 : kHeads;
   __shared__ float red[kRedThreads / 32][kAcc][256 + 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -70,7 +71,7 @@ rows_reduce_kernel(const __nv_bfloat16* __restrict__ x, long long M, long long s
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < kRedThreads / 32; ++w) s += red[w][o][c];
-    atomicAdd(outs + o * 256 + c, s);
+    if (c < ncols) atomicAdd(outs + o * out_row_stride + c, s);
   }
   if (kHeads > 0 && dsum != nullptr && lane == 0) {
     // every warp saw different rows, every lane of a warp the same d values
@@ -89,28 +90,29 @@ extern "C" int ffn_colsum_bf16(const void* x, int32_t num_slots, int64_t M, floa
   CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)num_slots * 256 * sizeof(float), stream));
   dim3 grid((unsigned)((M + kRedStrip - 1) / kRedStrip), (unsigned)num_slots);
   rows_reduce_kernel<0><<<grid, kRedThreads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), M,
-                                                          (long long)M * 256, nullptr, 0, out, 256, nullptr);
+                                                          (long long)M * 256, nullptr, 0, out, 256, nullptr, 256, 256);
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
 extern "C" int ffn_head_wgrad(const float* d_raw, int32_t first_head, int32_t num_heads, const void* h, int64_t M,
-                              float* out_w, float* out_b, void* stream_) {
+                              float* out_w, float* out_b, int32_t num_cols, void* stream_) {
   using namespace ffn;
-  if (!d_raw || !h || !out_w || !out_b || first_head < 0 || num_heads < 1 || first_head + num_heads > 4 || M < 0)
+  if (!d_raw || !h || !out_w || !out_b || first_head < 0 || num_heads < 1 || first_head + num_heads > 4 || M < 0 ||
+      num_cols < 1 || num_cols > 256)
     return fail("ffn_head_wgrad: bad argument");
   cudaStream_t stream = (cudaStream_t)stream_;
-  CUDA_TRY(cudaMemsetAsync(out_w, 0, (size_t)num_heads * 256 * sizeof(float), stream));
+  CUDA_TRY(cudaMemsetAsync(out_w, 0, (size_t)num_heads * num_cols * sizeof(float), stream));
   CUDA_TRY(cudaMemsetAsync(out_b, 0, (size_t)num_heads * sizeof(float), stream));
   if (M == 0) return 0;
   dim3 grid((unsigned)((M + kRedStrip - 1) / kRedStrip), 1);
   const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(h);
   switch (num_heads) {
-    case 1: rows_reduce_kernel<1><<<grid, kRedThreads, 0, stream>>>(hp, M, 0, d_raw, first_head, out_w, 0, out_b); break;
-    case 2: rows_reduce_kernel<2><<<grid, kRedThreads, 0, stream>>>(hp, M, 0, d_raw, first_head, out_w, 0, out_b); break;
-    case 3: rows_reduce_kernel<3><<<grid, kRedThreads, 0, stream>>>(hp, M, 0, d_raw, first_head, out_w, 0, out_b); break;
-    default: rows_reduce_kernel<4><<<grid, kRedThreads, 0, stream>>>(hp, M, 0, d_raw, first_head, out_w, 0, out_b); break;
+    case 1: rows_reduce_kernel<1><<<grid, kRedThreads, 0, stream>>>(hp, M, 0, d_raw, first_head, out_w, 0, out_b, num_cols, num_cols); break;
+    case 2: rows_reduce_kernel<2><<<grid, kRedThreads, 0, stream>>>(hp, M, 0, d_raw, first_head, out_w, 0, out_b, num_cols, num_cols); break;
+    case 3: rows_reduce_kernel<3><<<grid, kRedThreads, 0, stream>>>(hp, M, 0, d_raw, first_head, out_w, 0, out_b, num_cols, num_cols); break;
+    default: rows_reduce_kernel<4><<<grid, kRedThreads, 0, stream>>>(hp, M, 0, d_raw, first_head, out_w, 0, out_b, num_cols, num_cols); break;
   }
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());

@@ -159,14 +159,20 @@ class ImageDataset(torch.utils.data.Dataset, RayDataset):
         if (self.fused_loss and pred.is_cuda and pred.dtype == torch.float32 and self.colors.device == pred.device
                 and rays.rays.device == pred.device and rays.rays.dtype == torch.int64 and len(pred) > 0):
             from .autograd import MSELoss
-            use_alpha = self.alphas is not None and self.mode != Mode.Dilate
-            return MSELoss.apply(pred, render.alpha if use_alpha else None, self.colors,
-                                 self.alphas if use_alpha else None, rays.rays.contiguous(), self.alpha_weight)
+            colors, alphas, weight = self.loss_tables()
+            return MSELoss.apply(pred, render.alpha if alphas is not None else None, colors, alphas,
+                                 rays.rays.contiguous(), weight)
         actual = self.render(rays).to(render.device)
         color_loss = (actual.color - render.color).square().mean()
         if self.alpha_weight > 0 and actual.alpha is not None:
             return color_loss + self.alpha_weight * (actual.alpha - render.alpha).square().mean()
         return color_loss
+
+    def loss_tables(self):
+        """(colors (N,3), alphas (N,) or None, alpha_weight) as ``loss`` uses them: no alpha term and no zeroing of
+        the background colour without an alpha channel or in Dilate mode (image_dataset.py:253-260)."""
+        use_alpha = self.alphas is not None and self.mode != Mode.Dilate
+        return self.colors, (self.alphas if use_alpha else None), self.alpha_weight
 
     def _mode_index(self):
         return {Mode.Center: self.crop_index, Mode.Sparse: self.sparse_index,

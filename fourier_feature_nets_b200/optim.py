@@ -8,6 +8,7 @@ CPU implementation -- on a CPU model ``Raycaster.fit`` uses the PyTorch calls of
 from __future__ import annotations
 
 import ctypes
+import math
 from ctypes import c_float, c_int32, c_int64, c_void_p
 
 import torch
@@ -23,7 +24,7 @@ class AdamTensor(ctypes.Structure):
 def _bind(L):
     if getattr(L, "_optim_bound", False):
         return
-    L.ffn_clip_adam.argtypes = [ctypes.POINTER(AdamTensor), c_int32] + [c_float] * 9 + [c_void_p, c_void_p]
+    L.ffn_clip_adam.argtypes = [ctypes.POINTER(AdamTensor), c_int32] + [c_float] * 9 + [c_void_p, c_int32, c_void_p]
     L._optim_bound = True
 
 
@@ -43,7 +44,7 @@ class ClipAdam(torch.optim.Optimizer):
 
     def total_norm(self) -> float:
         """Norm of the value-clipped gradients of the last step (one device->host read)."""
-        return float(self._norm_sq.sqrt().item()) if self._norm_sq is not None else float("nan")
+        return math.sqrt(float(self._norm_sq[0].item())) if self._norm_sq is not None else float("nan")
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -72,6 +73,7 @@ class ClipAdam(torch.optim.Optimizer):
                 AdamTensor(p.data_ptr(), 0, self.state[p]["exp_avg"].data_ptr(), self.state[p]["exp_avg_sq"].data_ptr(),
                            p.numel()) for p in params])
             self._key = key
+            self._need = 1 + sum((p.numel() + 2047) // 2048 for p in params)
         arr = self._arr
         step = self.state[params[0]]["step"] + 1
         for i, p in enumerate(params):
@@ -82,11 +84,12 @@ class ClipAdam(torch.optim.Optimizer):
             arr[i].param, arr[i].grad = p.data_ptr(), g.data_ptr()
             arr[i].exp_avg, arr[i].exp_avg_sq = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
             st["step"] = step
-        if self._norm_sq is None or self._norm_sq.device != device:
-            self._norm_sq = torch.zeros((1,), dtype=torch.float32, device=device)
+        if self._norm_sq is None or self._norm_sq.device != device or self._norm_sq.numel() < self._need:
+            self._norm_sq = torch.zeros((max(self._need, 1024),), dtype=torch.float32, device=device)
         beta1, beta2 = group["betas"]
         with _lib.on_device(device):
             _lib._check(L.ffn_clip_adam(arr, len(params), group["clip_value"], group["max_norm"], group["lr"], beta1,
                                         beta2, group["eps"], group["weight_decay"], 1.0 - beta1 ** step,
-                                        1.0 - beta2 ** step, self._norm_sq.data_ptr(), _lib._stream()), "ffn_clip_adam")
+                                        1.0 - beta2 ** step, self._norm_sq.data_ptr(), self._norm_sq.numel(), _lib._stream()),
+                        "ffn_clip_adam")
         return loss

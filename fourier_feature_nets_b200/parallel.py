@@ -43,6 +43,16 @@ def allreduce_gradients(model: torch.nn.Module, average: bool = True):
     grads = [p.grad for p in model.parameters() if p.requires_grad and p.grad is not None]
     if not grads:
         return
+    # the training kernels write every gradient into one flat buffer and autograd hands the views on as .grad:
+    # all-reduce that buffer in place (no gather / scatter copies)
+    flat = model.__dict__.get("_ffn_flat_grad")
+    if flat is not None:
+        base = flat.untyped_storage().data_ptr()
+        if all(g.untyped_storage().data_ptr() == base for g in grads):
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            if average:
+                flat /= ws
+            return
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     if average:

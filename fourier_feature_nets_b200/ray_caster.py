@@ -32,6 +32,7 @@ class Raycaster(nn.Module):
         self.model = model
         self.check_nan_every_call = False   # True: reference behaviour (a host sync per render)
         self.train_kernels = True           # False: differentiate the plain PyTorch definition instead
+        self.fused_trainer = True           # False: fit() steps through autograd even where the C trainer applies
         self._lin_cache = {}
 
     # ---- the hot path -----------------------------------------------------------------
@@ -180,10 +181,23 @@ class Raycaster(nn.Module):
         on_cuda = next(self.model.parameters()).is_cuda
         # same update rule as ray_caster.py:283,327-329; on a GPU both clips and Adam are two launches (optim.ClipAdam)
         fused_step = on_cuda and self.train_kernels
+        trainer = None
+        device = next(self.model.parameters()).device
+        if on_cuda:       # ground truth, index tables and ray tables live in HBM for the whole run
+            for ds in (train_dataset, val_dataset, trainval):
+                if hasattr(ds, "to"):
+                    ds.to(device)
         if fused_step:
+            from . import trainer as _trainer
             from .optim import ClipAdam
-            optim = ClipAdam(self.model.parameters(), learning_rate, weight_decay=weight_decay, clip_value=0.1,
-                             max_norm=0.1)
+            if (self.fused_trainer and _trainer.supported(self.model) and hasattr(train_dataset, "loss_tables")
+                    and getattr(train_dataset, "fused_loss", False)):
+                # the whole step as two C calls (trainer.FusedTrainer); it doubles as the "optimizer" of the loop
+                optim = trainer = _trainer.FusedTrainer(self.model, learning_rate, weight_decay=weight_decay,
+                                                        clip_value=0.1, max_norm=0.1)
+            else:
+                optim = ClipAdam(self.model.parameters(), learning_rate, weight_decay=weight_decay, clip_value=0.1,
+                                 max_norm=0.1)
         else:
             optim = torch.optim.Adam(self.model.parameters(), learning_rate, weight_decay=weight_decay)
         step, epoch, log = 0, 0, []
@@ -207,15 +221,24 @@ class Raycaster(nn.Module):
                     break
                 exponential_lr_decay(optim, learning_rate, step, decay_rate, decay_steps)
                 batch = index[start:min(start + batch_size, num_rays)].tolist()
-                optim.zero_grad()
-                loss = self._loss(step, train_dataset, batch)
-                loss.backward()
-                if grad_sync is not None:
-                    grad_sync(self.model)
-                if not fused_step:
-                    torch.nn.utils.clip_grad_value_(self.model.parameters(), 0.1)
-                    torch.nn.utils.clip_grad_norm_(self.model.parameters(), 0.1)
-                optim.step()
+                if trainer is not None:
+                    rays = train_dataset.get_rays(batch, step).to(device)
+                    if len(rays.rays) > 0:      # (an all-background batch is a NaN loss in the reference)
+                        colors, alphas, weight = train_dataset.loss_tables()
+                        trainer.backward(rays, colors, alphas, weight, self._lin(train_dataset.num_samples, device))
+                        if grad_sync is not None:
+                            grad_sync(self.model)
+                        trainer.update()
+                else:
+                    optim.zero_grad()
+                    loss = self._loss(step, train_dataset, batch)
+                    loss.backward()
+                    if grad_sync is not None:
+                        grad_sync(self.model)
+                    if not fused_step:
+                        torch.nn.utils.clip_grad_value_(self.model.parameters(), 0.1)
+                        torch.nn.utils.clip_grad_norm_(self.model.parameters(), 0.1)
+                    optim.step()
 
                 if step < 10 or step % report_interval == 0:
                     epoch += 1

@@ -191,9 +191,10 @@ int ffn_colsum_bf16(const void* x, int32_t num_slots, int64_t num_points, float*
 
 /* Gradients of a 1..4-row head evaluated on CUDA cores (opacity_out nerf_model.py:118, color_out :123, final Linear
  * fourier_feature_models.py:77): out_w[o][c] = sum_m d_raw[m][first_head+o] * h[m][c] (h (M,256) bf16, fp32 accumulate),
- * out_b[o] = sum_m d_raw[m][first_head+o];  out_w (num_heads,256), out_b (num_heads). */
+ * out_b[o] = sum_m d_raw[m][first_head+o];  out_w (num_heads, num_cols) keeps the first num_cols <= 256 columns
+ * (color_out reads the 128 hidden_view channels), out_b (num_heads). */
 int ffn_head_wgrad(const float* d_raw, int32_t first_head, int32_t num_heads, const void* h, int64_t num_points,
-                   float* out_w, float* out_b, void* stream);
+                   float* out_w, float* out_b, int32_t num_cols, void* stream);
 
 /* Weight (and bias) gradients of every MMA layer in ONE launch: dW[out][in] += sum_rows dz[row][out] * x[row][in]
  * (autograd of nn.Linear inside Raycaster.fit, ray_caster.py:319-326; layers nerf_model.py:111-123,
@@ -224,8 +225,10 @@ int ffn_wgrad(const ffn_wgrad_tensor_t* tensors, int32_t n_tensors, const ffn_wg
 
 /* Optimiser step of Raycaster.fit (ray_caster.py:327-329) in two launches: clip_grad_value_(clip_value) ->
  * clip_grad_norm_(max_norm) (both written back into grad, <= 0 disables) -> torch.optim.Adam update with L2
- * weight decay.  bias_correction{1,2} = 1 - beta{1,2}^step.  norm_sq (device float[1]) receives the squared
- * total norm of the value-clipped gradients.  All tensors fp32, contiguous, on the current device. */
+ * weight decay.  bias_correction{1,2} = 1 - beta{1,2}^step.  norm_scratch (device float[norm_scratch_floats], at least
+ * 1 + sum ceil(numel / 2048)): [0] receives the squared total norm of the value-clipped gradients, the rest holds
+ * per-block partial sums that are added in a fixed order (deterministic: data-parallel replicas stay bit-identical).
+ * All tensors fp32, contiguous, on the current device. */
 typedef struct {
   float* param;
   float* grad;
@@ -235,7 +238,7 @@ typedef struct {
 } ffn_adam_tensor_t;
 int ffn_clip_adam(const ffn_adam_tensor_t* tensors, int32_t n, float clip_value, float max_norm, float lr,
                   float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
-                  float bias_correction2, float* norm_sq, void* stream);
+                  float bias_correction2, float* norm_scratch, int32_t norm_scratch_floats, void* stream);
 
 /* Loss of Raycaster.fit and its gradient in one launch (ImageDataset.render/.loss, image_dataset.py:224-262):
  * loss = mean((colors[rays] - color)^2) + alpha_weight * mean((alphas[rays] - alpha)^2), ground-truth colour zeroed
@@ -244,6 +247,42 @@ int ffn_clip_adam(const ffn_adam_tensor_t* tensors, int32_t n, float clip_value,
 int ffn_mse_loss(const float* color, const float* alpha, const float* gt_colors, const float* gt_alphas,
                  const int64_t* rays, int64_t num_rays, float alpha_weight, float* loss, float* grad_color,
                  float* grad_alpha, void* stream);
+
+/* ---- One optimisation step of Raycaster.fit (ray_caster.py:319-329) driven from C: the ~12 launches of a step
+ * issued back to back without interpreter time in between.  NeRF nets.  The caller owns every buffer:
+ *   weights/biases   the fp32 parameters in ffn_net_pack order
+ *   flat_grad        one fp32 buffer receiving every gradient at weight_grad_offset[i] / bias_grad_offset[i]
+ *                    (floats; parameter layout (out,in) row-major) -- all-reduce it between the two calls for
+ *                    data-parallel training
+ *   exp_avg, exp_avg_sq   Adam state, same layout as flat_grad, zero-initialised
+ *   workspace        >= ffn_trainer_workspace_bytes(net, num_rays, num_samples) bytes, 256-byte aligned */
+typedef struct ffn_trainer ffn_trainer_t;
+typedef struct {
+  int32_t num_linear;
+  float* const* weights;
+  float* const* biases;
+  const int64_t* weight_grad_offset;
+  const int64_t* bias_grad_offset;
+  float* flat_grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t flat_floats;
+} ffn_trainer_desc_t;
+int ffn_trainer_create(ffn_net_t* net, const ffn_trainer_desc_t* desc, ffn_trainer_t** out);
+void ffn_trainer_destroy(ffn_trainer_t* trainer);
+int64_t ffn_trainer_workspace_bytes(const ffn_net_t* net, int64_t num_rays, int32_t num_samples);
+/* forward (inputs as ffn_train_forward: samples OR rays) + ffn_mse_loss against gt tables indexed by rays + every
+ * gradient into flat_grad.  loss: device float[1]. */
+int ffn_trainer_backward(ffn_trainer_t* trainer, const float* positions, const float* view_directions,
+                         const float* t_values, const float* starts, const float* directions, const float* near,
+                         const float* far, const float* lin, const float* jitter, int32_t stratified, uint64_t seed,
+                         int64_t num_rays, int32_t num_samples, const float* gt_colors, const float* gt_alphas,
+                         const int64_t* rays, float alpha_weight, void* workspace, int64_t workspace_bytes, float* loss,
+                         int32_t* nan_flag, void* stream);
+/* ffn_clip_adam over all parameters + ffn_net_pack */
+int ffn_trainer_update(ffn_trainer_t* trainer, float clip_value, float max_norm, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, float bias_correction1, float bias_correction2,
+                       float* norm_scratch, int32_t norm_scratch_floats, void* stream);
 
 /* Debug: dump the float32 post-activation output of MMA layer `layer` (row-major (N,256))
  * for the first `n` points.  Used by the bring-up tests only. */

@@ -292,3 +292,56 @@ def test_fused_mse_loss_matches_the_elementwise_definition(R, use_alpha):
         assert (alpha.grad - ref_ga).abs().max().item() <= 1e-7
     else:
         assert alpha.grad is None
+
+
+def test_fused_trainer_equals_the_autograd_step():
+    """FusedTrainer (two C calls per step) runs the same kernels as render-under-autograd + MSELoss + ClipAdam: on
+    identical weights the gradients agree to the summation order of the wgrad atomics (1e-4 relative L2) and, fed the
+    same gradients, ``update`` and ``ClipAdam.step`` leave bit-identical parameters (deterministic norm reduction)."""
+    from fourier_feature_nets_b200.autograd import MSELoss
+    R, S, N = 300, 64, 4000
+    g = torch.Generator(device=DEV).manual_seed(9)
+    gt_c = torch.rand((N, 3), device=DEV, generator=g)
+    gt_a = (torch.rand((N,), device=DEV, generator=g) > 0.3).float()
+    a_model, b_model = trained_like_model(7), trained_like_model(7)
+    rc = ffn.Raycaster(a_model)
+    from fourier_feature_nets_b200.engine import _linear_list
+    ordered = [q for lin in _linear_list(a_model) for q in (lin.weight, lin.bias)]     # the trainer's tensor order:
+    opt = ffn.ClipAdam(ordered, 5e-4, weight_decay=1e-4, clip_value=0.1, max_norm=0.1)   # same fixed-order norm sum
+    trainer = ffn.FusedTrainer(b_model, 5e-4, weight_decay=1e-4, clip_value=0.1, max_norm=0.1)
+    lin = torch.linspace(0, 1, S).to(DEV)
+    for step in range(3):
+        bundle = make_batch(R, S, seed=step).to(DEV)
+        idx = torch.randint(0, N, (R,), device=DEV, generator=g)
+        bundle = ffn.RayBundle(bundle.starts, bundle.directions, bundle.near, bundle.far, idx, S, True, bundle.jitter)
+        opt.zero_grad()
+        out = rc.render(bundle, True)
+        loss_a = MSELoss.apply(out.color, out.alpha, gt_c, gt_a, idx, 0.1)
+        loss_a.backward()
+        before = _lib.launch_count()
+        loss_b = trainer.backward(bundle, gt_c, gt_a, 0.1, lin)
+        assert _lib.launch_count() - before >= 8
+        assert abs(loss_a.item() - loss_b.item()) <= 1e-6 * max(1.0, abs(loss_a.item()))
+        for (n, pa), pb in zip(a_model.named_parameters(), b_model.parameters()):
+            if pa.grad is None:          # the frozen encoding matrices
+                assert pb.grad is None
+                continue
+            da, db = pa.grad.flatten().double(), pb.grad.flatten().double()
+            assert ((da - db).norm() / (da.norm() + 1e-30)).item() <= 1e-4, (step, n)
+            pa.grad.copy_(pb.grad)       # same optimiser input on both sides from here on
+        opt.step()
+        trainer.update()
+        assert opt.total_norm() == trainer.total_norm()
+        for (n, pa), pb in zip(a_model.named_parameters(), b_model.parameters()):
+            assert torch.equal(pa, pb), (step, n, (pa - pb).abs().max().item())
+    # the re-packed tensor-core image follows the update: inference with both models agrees
+    with torch.no_grad():
+        probe = make_batch(64, 64, stratified=False).to(DEV)
+        ca = ffn.Raycaster(a_model).render(probe, False).color
+        cb = ffn.Raycaster(b_model).render(probe, False).color
+    assert (ca - cb).abs().max().item() <= 1e-3
+    # materialised samples take the same path
+    mat = make_batch(50, 32, seed=11).to(DEV).materialize()
+    mat = ffn.RaySamples(mat.positions, mat.view_directions, mat.t_values, torch.arange(50, device=DEV))
+    assert torch.isfinite(trainer.backward(mat, gt_c, None, 0.0, torch.linspace(0, 1, 32).to(DEV))).item()
+    trainer.update()

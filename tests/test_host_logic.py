@@ -207,6 +207,17 @@ torch.manual_seed(100); full = ffn.MLP(3, 4)
 ((full(x) - y) ** 2).sum().div(64).backward()
 err = max((a.grad - b.grad).abs().max().item() for a, b in zip(m.parameters(), full.parameters()))
 assert err < 1e-5, err
+# flat-buffer path (what the training kernels produce): .grad are views of one buffer registered on the model
+from fourier_feature_nets_b200.autograd import _flat_grads
+params = list(m.parameters())
+flat, views = _flat_grads(params, "cpu")
+for p, v in zip(params, views):
+    v.copy_(torch.full_like(v, float(rank + 1)))
+    p.grad = v
+m.__dict__["_ffn_flat_grad"] = flat
+parallel.allreduce_gradients(m, average=True)
+assert all(p.grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr() for p in params)
+assert all(torch.equal(p.grad, torch.full_like(p.grad, (1 + ws) / 2)) for p in params)
 print("rank", rank, "ok", err)
 dist.destroy_process_group()
 """
@@ -343,3 +354,13 @@ def test_engine_notices_fused_optimizer_steps():
     assert p._version == ver or True      # whichever torch does, the generation covers it
     engine.mark_weights_changed()
     assert engine._OPT_GENERATION[0] == gen + 2
+
+
+def test_no_undefined_names_in_the_package():
+    """The CUDA-only code paths cannot run in the CPU suite; at least every name they load must exist."""
+    import glob
+    files = glob.glob(os.path.join(ROOT, "fourier_feature_nets_b200", "*.py")) + \
+        glob.glob(os.path.join(ROOT, "tools", "*.py")) + [os.path.join(ROOT, "bench.py")]
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_names.py")] + files,
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout
