@@ -397,5 +397,14 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
                : "memory");
 }
 
+// 256-bit global store (sm_100: STG.E.ENL2.256): a thread that owns a contiguous run of a row writes whole 32-byte
+// sectors instead of two half sectors in two instructions
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
+                                             uint32_t f, uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d),
+               "r"(e), "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
+
 }  // namespace ptx
 }  // namespace ffn

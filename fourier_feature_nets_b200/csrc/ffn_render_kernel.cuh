@@ -183,25 +183,22 @@ __device__ __forceinline__ void store_act_block(const uint32_t (&v)[32], uint32_
   }
 }
 
-// training forward: bf16 copy (post-activation) of 32 columns of one row to HBM, and the sign word of
-// the accumulator block: bit (31-j) = 1 <=> column j is negative, i.e. ReLU'(.) = 0
-template <bool kRelu>
-__device__ __forceinline__ void save_block_global(const uint32_t (&v)[32], __nv_bfloat16* grow,
-                                                  uint32_t* gmask) {
-  uint4* dst = reinterpret_cast<uint4*>(grow);
+// training forward: bf16 copy (post-activation) of 32 columns of one row to HBM as two 32-byte stores; returns the
+// sign word of the accumulator block: bit (31-j) = 1 <=> column j is negative, i.e. ReLU'(.) = 0
+template <bool kRelu, bool kWantMask>
+__device__ __forceinline__ uint32_t save_block_global(const uint32_t (&v)[32], __nv_bfloat16* grow) {
+  uint32_t pk[16];
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
-    dst[q] = make_uint4(
-        ptx::pack2<true, kRelu>(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])),
-        ptx::pack2<true, kRelu>(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
-        ptx::pack2<true, kRelu>(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
-        ptx::pack2<true, kRelu>(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
-  if (gmask) {
-    uint32_t w = 0;
+  for (int q = 0; q < 16; ++q)
+    pk[q] = ptx::pack2<true, kRelu>(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+  ptx::st_global_v8(grow, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+  ptx::st_global_v8(grow + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+  uint32_t w = 0;
+  if constexpr (kWantMask) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) w = __funnelshift_l(v[j], w, 1);
-    *gmask = w;
   }
+  return w;
 }
 
 // backward: zero the columns whose forward pre-activation was negative (sign word from the forward)
@@ -244,11 +241,11 @@ __device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int b0,
     if constexpr (kPass == PASS_BWD) {
       if constexpr (kMask) apply_sign_mask(v, mwords[b]);
       store_act_block<true, false>(v, chunk_row, row7, u0);
-      if (valid && gh) save_block_global<false>(v, gh + b * 32, nullptr);
+      if (valid && gh) save_block_global<false, false>(v, gh + b * 32);
     } else {
       store_act_block<kBF16, kRelu>(v, chunk_row, row7, u0);
       if constexpr (kPass == PASS_TRAIN_FWD) {
-        if (valid && gh) save_block_global<kRelu>(v, gh + b * 32, (kRelu && gm) ? gm + b : nullptr);
+        if (valid && gh) mwords[b & 7] = save_block_global<kRelu, kRelu>(v, gh + b * 32);
       }
     }
   };
@@ -262,6 +259,16 @@ __device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int b0,
       ptx::tmem_ld64_wait(taddr_base + (uint32_t)b * 32u, v);
       one(reinterpret_cast<uint32_t(&)[32]>(v[0]), b);
       one(reinterpret_cast<uint32_t(&)[32]>(v[32]), b + 1);
+    }
+  }
+  if constexpr (kPass == PASS_TRAIN_FWD && kRelu) {
+    // the sign words of this warpgroup's blocks in one store (32 bytes for a 256-wide layer) instead of one
+    // 4-byte store per block
+    if (valid && gh && gm) {
+      if (nblk == 8)
+        ptx::st_global_v8(gm + b0, mwords[0], mwords[1], mwords[2], mwords[3], mwords[4], mwords[5], mwords[6], mwords[7]);
+      else
+        for (int i = 0; i < nblk; ++i) gm[b0 + i] = mwords[(b0 + i) & 7];
     }
   }
 }
@@ -665,7 +672,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           apply_sign_mask(v, valid ? __ldg(mw + b) : 0xffffffffu);
           store_act_block<true, false>(v, slot_base + (uint32_t)(b >> 1) * kChunkBytesA + row_off, row7,
                                        (uint32_t)(b & 1) * 4u);
-          if (valid) save_block_global<false>(v, gdz + c0, nullptr);
+          if (valid) save_block_global<false, false>(v, gdz + c0);
         }
         if (args.bwd_sigma_chunk) {
 #pragma unroll
@@ -860,8 +867,8 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
                 uint32_t* gm = (relu && ld.mask_idx >= 0)
                                    ? args.save_mask + ((size_t)ld.mask_idx * args.M + row_g) * 8 + b : nullptr;
                 // v still holds the raw accumulator (sign source); x holds the activated fp32 values
-                save_block_global<false>(reinterpret_cast<uint32_t(&)[32]>(x),
-                                         args.save_h + ((size_t)ld.save_idx * args.M + row_g) * 256 + c0, nullptr);
+                save_block_global<false, false>(reinterpret_cast<uint32_t(&)[32]>(x),
+                                                args.save_h + ((size_t)ld.save_idx * args.M + row_g) * 256 + c0);
                 if (gm) {
                   uint32_t w = 0;
 #pragma unroll

@@ -41,11 +41,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("report")
 ap.add_argument("--rays", type=int, default=0)
 ap.add_argument("--note", default="")
+ap.add_argument("--row", type=int, default=-1, help="which captured launch of the report (default: the last)")
 args = ap.parse_args()
 raw = subprocess.run(["ncu", "-i", args.report, "--page", "raw", "--csv"], check=True, capture_output=True,
                      text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, vals = rows[0], rows[1], rows[-1]
+hdr, units, vals = rows[0], rows[1], (rows[2:][args.row])
 out = {"report": args.report, "kernel": vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else ""}
 for h, u, v in zip(hdr, units, vals):
     if h in KEYS:

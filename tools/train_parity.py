@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--samples", type=int, default=64)
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--out", default="")
+    ap.add_argument("--operand", default="fp16")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     tmp = tempfile.mkdtemp()
@@ -46,6 +47,7 @@ def main():
         train = ffn.ImageDataset.load(data, "train", args.samples, True, True).to(dev)
         val = ffn.ImageDataset.load(data, "val", args.samples, True, False).to(dev)
         model = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True).to(dev)
+        model.ffn_operand = args.operand
         rc = ffn.Raycaster(model)
         rc.train_kernels = kernels
         warm = ffn.Raycaster(ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True).to(dev))     # one-time costs (module load, cuBLAS
