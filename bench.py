@@ -43,26 +43,36 @@ def parse():
     ap.add_argument("--rays", type=int, default=1 << 20, help="rays per step per GPU")
     ap.add_argument("--cameras", type=int, default=0, help="cameras in the ray pool (0 = enough for all steps)")
     ap.add_argument("--operand", default="fp16", choices=["fp16", "bf16"])
-    ap.add_argument("--cpu-rays", type=int, default=8192, help="rays in the bounded CPU sample")
+    ap.add_argument("--cpu-rays", type=int, default=8192, help="rays of the parity sample (numpy oracle)")
+    ap.add_argument("--ref-rays", type=int, default=32768, help="rays per step of the timed CPU reference sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs")
     return ap.parse_args()
 
 
-def lego_cameras(num, res=400):
-    """look-at cameras on the upper hemisphere, radius 4, fov_y 40 deg (orbit_video.py:21-24)."""
-    import fourier_feature_nets_b200 as ffn
-    from fourier_feature_nets_b200.utils import look_at_extrinsics
-    cams = []
+def lego_camera_matrices(num, res=400):
+    """(K (3,3), [E (4,4)]): look-at cameras on the upper hemisphere, radius 4, fov_y 40 deg (orbit_video.py:21-24);
+    camera-to-world, +z forward / +y down.  numpy only: shared by both arms."""
     focal = .5 * res / np.tan(.5 * 40 * np.pi / 180)
     K = np.array([[focal, 0, res / 2], [0, focal, res / 2], [0, 0, 1]], np.float32)
     golden = np.pi * (3 - np.sqrt(5))
+    exts = []
     for i in range(num):
         z = 0.15 + 0.8 * (i + 0.5) / num
         r = np.sqrt(1 - z * z)
         pos = 4.0 * np.array([r * np.cos(golden * i), z, r * np.sin(golden * i)])
-        ext = look_at_extrinsics(pos, np.array([0, 1.0, 0])).astype(np.float32)
-        cams.append(ffn.CameraInfo.create("cam%d" % i, ffn.Resolution(res, res), K, ext))
-    return cams
+        fwd = -pos / np.linalg.norm(pos)
+        right = np.cross(fwd, np.array([0, 1.0, 0]))
+        right /= np.linalg.norm(right)
+        ext = np.eye(4)
+        ext[:3, 0], ext[:3, 1], ext[:3, 2], ext[:3, 3] = right, np.cross(fwd, right), fwd, pos
+        exts.append(ext.astype(np.float32))
+    return K, exts
+
+
+def lego_cameras(num, res=400):
+    import fourier_feature_nets_b200 as ffn
+    K, exts = lego_camera_matrices(num, res)
+    return [ffn.CameraInfo.create("cam%d" % i, ffn.Resolution(res, res), K, e) for i, e in enumerate(exts)]
 
 
 def model_params_numpy(model):
@@ -73,6 +83,14 @@ def oracle_render(params, o, d, near, far, u, chunk=8192):
     import oracle
     samples = oracle.sample_rays(o, d, near, far, SAMPLES, u=u)
     return oracle.render_rays(lambda p, v: oracle.nerf_forward(params, p, v), samples, True, True, chunk)
+
+
+def torch_oracle_render(params, o, d, near, far, u):
+    """The reference's own ATen op sequence on the host cores (oracle/ffn_oracle_torch.py); params: name -> CPU tensor."""
+    import torch
+    from oracle import ffn_oracle_torch as ot
+    t = [torch.from_numpy(np.ascontiguousarray(a)) for a in (o, d, near, far, u)]
+    return ot.render_rays(params, t[0], t[1], t[2], t[3], SAMPLES, t[4], True, batch=4096)
 
 
 class ClockSampler(threading.Thread):
@@ -143,37 +161,35 @@ def ncu_traffic():
 
 
 def run_reference(args):
-    """The reference's algorithm on the host cores (numpy oracle port), same config."""
+    """The reference's CPU path on the host cores, same config: only ``oracle/`` (+ numpy / torch) runs here, nothing of
+    the product package."""
     import torch
+    import oracle
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import fourier_feature_nets_b200 as ffn
-    torch.manual_seed(20080524)
-    model = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True)
-    params = model_params_numpy(model)
-    sampler = ffn.RaySampler(np.diag([2, 2, 2, 1]).astype(np.float32), lego_cameras(1), SAMPLES, True)
-    valid = torch.nonzero(sampler.valid_mask).flatten().numpy()
-    n = min(args.cpu_rays, len(valid))
+    params = {k: torch.from_numpy(v) for k, v in oracle.init_nerf_params(seed=20080524).items()}
+    K_, exts = lego_camera_matrices(1)
+    xs, ys = np.meshgrid(np.arange(400), np.arange(400))
+    starts, directions = oracle.raycast(K_, exts[0], np.stack([xs, ys], -1).reshape(-1, 2))
+    nf, ok = oracle.near_far(np.diag([2, 2, 2, 1]).astype(np.float32), starts, directions)
+    valid = np.nonzero(ok)[0]
+    n = min(args.ref_rays, len(valid))
     rng = np.random.default_rng(0)
     times = []
     for step in range(args.warmup + args.steps):
         idx = rng.choice(valid, n, replace=False)
-        o, d = sampler.starts.numpy()[idx], sampler.directions.numpy()[idx]
-        near, far = sampler.near_far.numpy()[:, idx]
+        o, d = starts[idx].astype(np.float32), directions[idx].astype(np.float32)
+        near, far = nf[0, idx].astype(np.float32), nf[1, idx].astype(np.float32)
         u = rng.random((n, SAMPLES), dtype=np.float32)
         t0 = time.perf_counter()
-        oracle_render(params, o, d, near, far, u)
+        torch_oracle_render(params, o, d, near, far, u)
         dt = time.perf_counter() - t0
         if step >= args.warmup:
             times.append(dt)
     total = sum(times)
     value = n * len(times) / total
-    try:
-        from threadpoolctl import threadpool_info
-        cores = max([i["num_threads"] for i in threadpool_info()] + [1])
-    except Exception:
-        cores = os.cpu_count()
+    cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
@@ -181,8 +197,9 @@ def run_reference(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "rays_per_step": n, "samples_per_ray": SAMPLES},
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": "%d rays x %d samples per step, numpy oracle (oracle/ffn_oracle.py), "
-                                   "host cores: %d" % (n, SAMPLES, os.cpu_count())},
+                         "sample": "%d rays x %d samples per step in batches of 4096, the reference's ATen op sequence "
+                                   "on the host (oracle/ffn_oracle_torch.py), torch threads: %d of %d cores"
+                                   % (n, SAMPLES, cores, os.cpu_count())},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -318,9 +335,17 @@ def main():
             near, far = b.near[:n].numpy(), b.far[:n].numpy()
             u = np.random.default_rng(1).random((n, SAMPLES), dtype=np.float32)
             params = model_params_numpy(model)
-            oracle_render(params, o[:512], d[:512], near[:512], far[:512], u[:512])   # warm BLAS threads
+            ref = oracle_render(params, o, d, near, far, u)          # parity arbiter: the numpy oracle
+            # timed CPU baseline: the reference's ATen op sequence on the host cores, a bounded sample
+            nb_cpu = min(args.ref_rays, len(host_bundles[W].starts))
+            hb = host_bundles[W]
+            ucpu = np.random.default_rng(2).random((nb_cpu, SAMPLES), dtype=np.float32)
+            cpu_model = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+            cargs = (hb.starts[:nb_cpu].numpy(), hb.directions[:nb_cpu].numpy(), hb.near[:nb_cpu].numpy(),
+                     hb.far[:nb_cpu].numpy(), ucpu)
+            torch_oracle_render(cpu_model, *[a[:4096] for a in cargs])     # warm the thread pool
             t0 = time.perf_counter()
-            ref = oracle_render(params, o, d, near, far, u)
+            torch_oracle_render(cpu_model, *cargs)
             cpu_s = time.perf_counter() - t0
             with torch.no_grad():
                 bb = ffn.RayBundle(b.starts[:n], b.directions[:n], b.near[:n], b.far[:n], b.rays[:n], SAMPLES,
@@ -328,15 +353,12 @@ def main():
                 ours = rc.render(bb.to(dev), True).numpy()
             err = np.abs(ours.color - ref.color)
             mse = float(np.mean((ours.color - ref.color) ** 2))
-            try:
-                from threadpoolctl import threadpool_info
-                cores = max([i["num_threads"] for i in threadpool_info()] + [1])
-            except Exception:
-                cores = os.cpu_count()
+            cores = torch.get_num_threads()
             line["cpu_baseline"] = {
-                "value": n / cpu_s, "unit": "rays/s", "cores": cores, "kind": "port",
-                "sample": "%d rays x %d samples of the same workload, numpy oracle, host cores: %d"
-                          % (n, SAMPLES, os.cpu_count())}
+                "value": nb_cpu / cpu_s, "unit": "rays/s", "cores": cores, "kind": "port",
+                "sample": "%d rays x %d samples of the same workload in batches of 4096, the reference's ATen op "
+                          "sequence on the host (oracle/ffn_oracle_torch.py), torch threads: %d of %d cores"
+                          % (nb_cpu, SAMPLES, cores, os.cpu_count())}
             # the reference's op sequence (RaySamples -> NeRF.forward -> compositing, ray_caster.py:48-93) as plain
             # fp32 PyTorch on the SAME GPU, inference batches of 4096 rays like orbit_video.py:37 -- the "1-GPU
             # PyTorch" denominator of north_star's >= 10x target.  Bounded sample, device-resident inputs.
@@ -363,6 +385,37 @@ def main():
                 "sample": "%d batches of %d rays x %d samples, plain fp32 PyTorch ops of the reference definition on "
                           "the same GPU, samples already materialised in HBM" % (nb, tb, SAMPLES),
                 "color_max_abs_vs_ours": float((ours_t.color - ref_t.color).abs().max())}
+            # the training step of the same model (row a-14 of SURVEY.md section 8): FusedTrainer.backward + update at
+            # train_nerf.py's batch (1024 rays) x 128 samples; explanatory, not the headline metric
+            try:
+                tm = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True).to(dev)
+                tr = ffn.FusedTrainer(tm, 5e-4)
+                tb_r, tb_s = 1024, 128
+                tbun = dev_bundles[W].subset(range(0, tb_r))
+                tbun = ffn.RayBundle(tbun.starts, tbun.directions, tbun.near, tbun.far,
+                                     torch.arange(tb_r, device=dev), tb_s, True, None, seed=1)
+                gt_c, gt_a = torch.rand((tb_r, 3), device=dev), torch.rand((tb_r,), device=dev)
+                lin = torch.linspace(0, 1, tb_s).to(dev)
+                l0 = _lib.launch_count()
+                for _ in range(5):
+                    tr.backward(tbun, gt_c, gt_a, 0.1, lin)
+                    tr.update()
+                per_step = (_lib.launch_count() - l0) // 5
+                torch.cuda.synchronize()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                for _ in range(20):
+                    tr.backward(tbun, gt_c, gt_a, 0.1, lin)
+                    tr.update()
+                ev1.record()
+                torch.cuda.synchronize()
+                ms = ev0.elapsed_time(ev1) / 20
+                line["train_step"] = {"ms_per_step": ms, "rays_per_s": tb_r / ms * 1e3, "rays": tb_r, "samples": tb_s,
+                                      "kernel_launches_per_step": int(per_step),
+                                      "what": "forward-with-saves + loss + dgrad + wgrad + clip + Adam + re-pack "
+                                              "(FusedTrainer, two C calls)"}
+            except Exception as e:       # never lose the headline line over the explanatory leg
+                line["train_step"] = {"error": "%s: %s" % (type(e).__name__, e)}
             line["parity"] = {"rays": n, "color_max_abs": float(err.max()),
                               "alpha_max_abs": float(np.abs(ours.alpha - ref.alpha).max()),
                               "depth_mismatch_frac": float((ours.depth != ref.depth).mean()),

@@ -154,3 +154,50 @@ def test_determine_cdf_via_reference_cdfs():
     sigma = oracle.softplus(raw[:, 3]).reshape(-1, 16)
     cdf = oracle.determine_cdf(t, sigma)
     np.testing.assert_allclose(cdf, g["cdfs"], rtol=0, atol=5e-5)
+
+
+def test_torch_oracle_matches_reference_outputs():
+    """oracle/ffn_oracle_torch.py (what bench.py times as the reference's CPU path) runs the reference's own ATen op
+    sequence: raw outputs within fp32 GEMM blocking differences (the golden run used one 12,288-row batch), pixels
+    within 2e-5, and the compositing of the reference's raw outputs bit-identical."""
+    import torch
+    from oracle import ffn_oracle_torch as ot
+    g = load("nerf_render.npz")
+    p = {k: torch.from_numpy(v) for k, v in weights(g).items()}
+    assert torch.equal(ot.encoding_matrix(9.0, 10), p["pos_encoding"])
+    assert torch.equal(ot.encoding_matrix(3.0, 4), p["view_encoding"])
+    pos, view = torch.from_numpy(g["positions"]), torch.from_numpy(g["view_directions"])
+    with torch.no_grad():
+        raw = ot.nerf_forward(p, pos.reshape(-1, 3), view.reshape(-1, 3), pos_enc=p["pos_encoding"],
+                              view_enc=p["view_encoding"])
+    scale = np.abs(g["raw"]).max()
+    assert np.abs(raw.numpy() - g["raw"]).max() <= 2e-5 * max(1.0, scale)
+    out = ot.render(raw.reshape(192, 64, 4), torch.from_numpy(g["t_values"]), True)
+    np.testing.assert_allclose(out.color.numpy(), g["color"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(out.alpha.numpy(), g["alpha"], rtol=0, atol=2e-5)
+    out = ot.render(torch.from_numpy(g["raw"]).reshape(192, 64, 4), torch.from_numpy(g["t_values"]), True)
+    assert np.array_equal(out.color.numpy(), g["color"]) and np.array_equal(out.alpha.numpy(), g["alpha"])
+    assert np.array_equal(out.depth.numpy(), g["depth"])
+
+
+def test_torch_oracle_sampling_and_agreement_with_the_numpy_oracle():
+    import torch
+    from oracle import ffn_oracle_torch as ot
+    g = load("sampler.npz")
+    rng = np.random.default_rng(3)
+    R, S = 64, 64
+    o = np.tile(np.array([[0.2, -0.1, -4.0]], np.float32), (R, 1))
+    d = rng.normal(size=(R, 3)).astype(np.float32) * 0.15 + np.array([0, 0, 1], np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    near, far = np.full(R, 3.0, np.float32) + rng.random(R, dtype=np.float32), np.full(R, 5.5, np.float32)
+    u = rng.random((R, S), dtype=np.float32)
+    ref = oracle.sample_rays(o, d, near, far, S, u=u)
+    pos, dirs, t = ot.sample_rays(*[torch.from_numpy(a) for a in (o, d, near, far)], S, torch.from_numpy(u))
+    assert np.array_equal(t.numpy(), ref.t_values) and np.array_equal(pos.numpy(), ref.positions)
+    params = oracle.init_nerf_params(seed=1, gain=2.0)
+    want = oracle.render_rays(lambda p, v: oracle.nerf_forward(params, p, v), ref)
+    tp = {k: torch.from_numpy(v) for k, v in params.items()}
+    got = ot.render_rays(tp, *[torch.from_numpy(a) for a in (o, d, near, far)], S, torch.from_numpy(u), True, batch=48)
+    np.testing.assert_allclose(got.color.numpy(), want.color, rtol=0, atol=3e-5)
+    np.testing.assert_allclose(got.alpha.numpy(), want.alpha, rtol=0, atol=3e-5)
+    assert g is not None
