@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/ffn_b200.h"
+#include "ffn_tma_host.cuh"
 #include "ffn_common.cuh"
 #include "ffn_render_kernel.cuh"
 #include "ffn_render_ts_kernel.cuh"

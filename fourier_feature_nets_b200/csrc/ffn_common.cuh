@@ -1,5 +1,6 @@
 // Shared definitions for libffn_b200 (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -142,6 +143,8 @@ struct KernelArgs {
   int32_t bwd_sigma_chunk;     //           1: d(sigma_raw) goes to column 0 of the encoding chunk
   int32_t num_tiles;
   int32_t lockstep;            // 1: both slots run the same layer and share each weight stage (see kernel)
+  int32_t dz_tma;              // PASS_BWD: 1 = dz_out is written by TMA stores of the bf16 A tile (dz_map)
+  alignas(64) CUtensorMap dz_map;   // [n_dz][M][256] bf16, boxes of 64 columns x 32 rows, SWIZZLE_128B
 };
 
 }  // namespace ffn

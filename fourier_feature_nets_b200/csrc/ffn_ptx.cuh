@@ -406,5 +406,17 @@ __device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, ui
                : "memory");
 }
 
+// TMA tensor store shared -> global (3-D map), bulk async-group completion
+__device__ __forceinline__ void tma_store_3d(const void* map, uint32_t src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(src_smem)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed entirely (writes performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 }  // namespace ptx
 }  // namespace ffn

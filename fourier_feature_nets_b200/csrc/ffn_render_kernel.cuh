@@ -658,6 +658,10 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
         const int nb0 = args.bwd_first_cols >> 5;
         const uint32_t* mw = args.save_mask + ((size_t)args.bwd_first_mask * args.M + (valid ? row_g : 0)) * 8;
         __nv_bfloat16* gdz = args.dz_out + ((size_t)args.bwd_first_save * args.M + (valid ? row_g : 0)) * 256;
+        if (args.dz_tma) {      // the previous tile's TMA stores must have read this warp's rows of the A tile
+          if (lane == 0) ptx::bulk_wait_read_all();
+          __syncwarp();
+        }
         for (int b = 0; b < nb0; ++b) {
           uint32_t v[32];
           const int c0 = b * 32;
@@ -672,7 +676,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           apply_sign_mask(v, valid ? __ldg(mw + b) : 0xffffffffu);
           store_act_block<true, false>(v, slot_base + (uint32_t)(b >> 1) * kChunkBytesA + row_off, row7,
                                        (uint32_t)(b & 1) * 4u);
-          if (valid) save_block_global<false, false>(v, gdz + c0);
+          if (valid && !args.dz_tma) save_block_global<false, false>(v, gdz + c0);
         }
         if (args.bwd_sigma_chunk) {
 #pragma unroll
@@ -756,6 +760,15 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
         else ptx::mbar_arrive(my_a_ready);
       }
 
+      if constexpr (kPass == PASS_BWD) {
+        // dz of the first (CUDA-core) layer: this warp's 32 rows of every 64-column chunk, straight from the A tile
+        if (args.dz_tma && grp == 0 && lane == 0) {
+          for (int c = 0; c < (args.bwd_first_cols >> 6); ++c)
+            ptx::tma_store_3d(&args.dz_map, slot_base + (uint32_t)c * kChunkBytesA + (uint32_t)(wq * 32) * 128u, 64 * c,
+                              (int)(tile * kTileM) + wq * 32, args.bwd_first_save);
+          ptx::bulk_commit_group();
+        }
+      }
       float out[4] = {0.f, 0.f, 0.f, 0.f};  // raw rgb | sigma of this sample
 
       if (eprof) { const long long n = clock64(); e_front += n - e_t0; e_t = n; }
@@ -777,8 +790,13 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
         } else if (ld.epi == EPI_BWD_LINEAR || ld.epi == EPI_BWD_MASK) {
           if constexpr (kPass == PASS_BWD) {
             const size_t rg = valid ? (size_t)row_g : 0;
-            __nv_bfloat16* gh = ld.save_idx >= 0 ? args.dz_out + ((size_t)ld.save_idx * args.M + rg) * 256 : nullptr;
+            __nv_bfloat16* gh = (ld.save_idx >= 0 && !args.dz_tma) ? args.dz_out + ((size_t)ld.save_idx * args.M + rg) * 256
+                                                                  : nullptr;
             uint32_t* gm = ld.mask_idx >= 0 ? args.save_mask + ((size_t)ld.mask_idx * args.M + rg) * 8 : nullptr;
+            if (args.dz_tma) {      // earlier TMA stores of this warp have finished reading the rows it overwrites now
+              if (lane == 0) ptx::bulk_wait_read_all();
+              __syncwarp();
+            }
             if (ld.epi == EPI_BWD_MASK)
               lean_layer_epilogue<true, false, PASS_BWD, true>(taddr_base, blk0, nblk_grp, slot_base + row_off, row7, gh, gm, valid);
             else
@@ -913,6 +931,20 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
             else ptx::mbar_arrive(my_a_ready);
           }
         }
+        if constexpr (kPass == PASS_BWD) {
+          if (args.dz_tma && ld.save_idx >= 0 && (ld.epi == EPI_BWD_LINEAR || ld.epi == EPI_BWD_MASK)) {
+            if (l == L - 1) {      // no UMMA reads the last tile: publish it to the async proxy for the store alone
+              ptx::fence_proxy_async();
+              __syncwarp();
+            }
+            if (lane == 0) {
+              for (int c = 0; c < 4; ++c)
+                ptx::tma_store_3d(&args.dz_map, slot_base + (uint32_t)c * kChunkBytesA + (uint32_t)(wq * 32) * 128u,
+                                  64 * c, (int)(tile * kTileM) + wq * 32, ld.save_idx);
+              ptx::bulk_commit_group();
+            }
+          }
+        }
         if (l == 0 && pend && grp == 0) {
           // the previous tile of this slot: composite it now, under the tensor core's work on layer 1
           finish_tile(p_out, p_tval, p_sidx, p_ray, p_row_g, p_valid);
@@ -947,6 +979,9 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       }
     }
     if (pend) finish_tile(p_out, p_tval, p_sidx, p_ray, p_row_g, p_valid);
+    if constexpr (kPass == PASS_BWD) {
+      if (args.dz_tma && lane == 0) ptx::bulk_wait_all();     // the stores source this CTA's shared memory
+    }
     if (eprof) {
       atomicAdd(args.stats + 4, (unsigned long long)e_wait);
       atomicAdd(args.stats + 5, (unsigned long long)e_work);

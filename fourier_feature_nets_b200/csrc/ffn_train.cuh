@@ -328,5 +328,11 @@ extern "C" int ffn_train_backward(ffn_net_t* net, const float* d_raw, const void
   ka.mode = MODE_POINTS; ka.M = M; ka.S = 1; ka.fused = 0; ka.dbg_layer = -1;
   ka.d_raw = d_raw; ka.save_mask = (uint32_t*)save_mask; ka.dz_out = (__nv_bfloat16*)dz_out;
   fill_train_common(net, ka);
+  // dz leaves the kernel as TMA stores of the bf16 A tile (32-row x 64-column boxes per epilogue warp) instead of
+  // row-per-thread global stores; FFN_DZ_TMA=0 keeps the latter.  The row coordinate of a box is a 32-bit int.
+  static const bool want_tma = !(getenv("FFN_DZ_TMA") && atoi(getenv("FFN_DZ_TMA")) == 0);
+  if (want_tma && M < (1ll << 31) - 256 && (reinterpret_cast<uintptr_t>(dz_out) & 15) == 0 &&
+      ffn_encode_bf16_3d(&ka.dz_map, dz_out, M, 256, net->n_dz, 32) == 0)
+    ka.dz_tma = 1;
   return launch_render(net, ka, (cudaStream_t)stream_, PASS_BWD);
 }

@@ -240,22 +240,6 @@ __global__ void __launch_bounds__(kWgThreads, 1) ffn_wgrad_kernel(const __grid_c
 // ============================================================================================
 // host side
 // ============================================================================================
-typedef CUresult (*ffn_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static ffn_encode_tiled_fn wgrad_encode_fn() {
-  static ffn_encode_tiled_fn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<ffn_encode_tiled_fn>(p);
-  }
-  return fn;
-}
-
 extern "C" int ffn_wgrad(const ffn_wgrad_tensor_t* tensors, int32_t n_tensors, const ffn_wgrad_job_t* jobs,
                          int32_t n_jobs, void* stream_) {
   using namespace ffn;
@@ -265,8 +249,7 @@ extern "C" int ffn_wgrad(const ffn_wgrad_tensor_t* tensors, int32_t n_tensors, c
   cudaStream_t stream = (cudaStream_t)stream_;
   const int64_t M = tensors[0].rows;
   if (M == 0) return 0;
-  ffn_encode_tiled_fn encode = wgrad_encode_fn();
-  if (!encode) return fail("ffn_wgrad: cuTensorMapEncodeTiled is not available from the driver");
+  if (!ffn_encode_fn()) return fail("ffn_wgrad: cuTensorMapEncodeTiled is not available from the driver");
   static WgParams P;   // 4.6 KB; the launch copies it
   static bool attr_set = false;
   if (!attr_set) {
@@ -285,14 +268,8 @@ extern "C" int ffn_wgrad(const ffn_wgrad_tensor_t* tensors, int32_t n_tensors, c
     if (!T.ptr || T.rows != M || T.cols < 64 || (T.cols & 63) || T.slots < 1 || (reinterpret_cast<uintptr_t>(T.ptr) & 15))
       return fail("ffn_wgrad: every tensor must be [slots][rows][cols] bf16, cols a multiple of 64, the same rows, "
                   "16-byte aligned");
-    const cuuint64_t gdim[3] = {(cuuint64_t)T.cols, (cuuint64_t)M, (cuuint64_t)T.slots};
-    const cuuint64_t gstr[2] = {(cuuint64_t)T.cols * 2, (cuuint64_t)T.cols * 2 * (cuuint64_t)M};
-    const cuuint32_t box[3] = {64, (cuuint32_t)kWgKTile, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(&P.maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
-                        const_cast<void*>(T.ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail("ffn_wgrad: cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    const int r = ffn_encode_bf16_3d(&P.maps[i], T.ptr, M, T.cols, T.slots, kWgKTile);
+    if (r != 0) return fail("ffn_wgrad: cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
   }
   const int ktiles = (int)((M + kWgKTile - 1) / kWgKTile);
   double cost[kWgMaxJobs], total = 0;
