@@ -1,7 +1,7 @@
 """Differentiable ``Raycaster.render`` on the CUDA kernels (training step).
 
 forward   ``ffn_train_forward``      fused sampling/encoding/MLP/compositing that also spills what the
-                                     backward needs: bf16 layer outputs, ReLU sign words, encoding rows,
+                                     backward needs: 16-bit layer outputs (operand dtype), ReLU sign words, encoding rows,
                                      raw network outputs and t values
 backward  ``ffn_composite_backward`` d(loss)/d(color, alpha) -> d(loss)/d(raw rgb, sigma) per sample
           ``ffn_train_backward``     the dgrad chain on tcgen05 (transposed bf16 weights) -> dz per layer
@@ -27,7 +27,7 @@ from . import engine as _engine
 
 
 class WgradTensor(ctypes.Structure):
-    _fields_ = [("ptr", c_void_p), ("rows", c_int64), ("cols", c_int32), ("slots", c_int32)]
+    _fields_ = [("ptr", c_void_p), ("rows", c_int64), ("cols", c_int32), ("slots", c_int32), ("fp16", c_int32)]
 
 
 class WgradJob(ctypes.Structure):
@@ -51,7 +51,8 @@ def _bind(L):
                                          c_void_p]
     L.ffn_train_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
     L.ffn_colsum_bf16.argtypes = [c_void_p, c_int32, c_int64, c_void_p, c_void_p]
-    L.ffn_head_wgrad.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p]
+    L.ffn_head_wgrad.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32,
+                                 c_void_p]
     L._train_bound = True
 
 
@@ -71,14 +72,14 @@ def _head_grads(L, d_raw: torch.Tensor, first: int, count: int, h: torch.Tensor,
     """Gradients of a CUDA-core head into gw (count, cols <= 256), gb (count,):
     gw = d_raw[:, first:first+count]^T @ h[:, :cols], fp32 accumulation."""
     M = d_raw.shape[0]
-    _lib._check(L.ffn_head_wgrad(_p(d_raw), first, count, _p(h), M, _p(gw), _p(gb), gw.shape[1], _lib._stream()),
-                "ffn_head_wgrad")
+    _lib._check(L.ffn_head_wgrad(_p(d_raw), first, count, _p(h), M, _p(gw), _p(gb), gw.shape[1],
+                                 int(h.dtype == torch.float16), _lib._stream()), "ffn_head_wgrad")
 
 
 def _wg_tensor(t: torch.Tensor) -> WgradTensor:
-    """(slots, rows, cols) bf16 tensor -> descriptor."""
-    assert t.dim() == 3 and t.is_contiguous() and t.dtype == torch.bfloat16
-    return WgradTensor(t.data_ptr(), t.shape[1], t.shape[2], t.shape[0])
+    """(slots, rows, cols) bf16 / fp16 tensor -> descriptor."""
+    assert t.dim() == 3 and t.is_contiguous() and t.dtype in (torch.bfloat16, torch.float16)
+    return WgradTensor(t.data_ptr(), t.shape[1], t.shape[2], t.shape[0], int(t.dtype == torch.float16))
 
 
 def _wg_job(a_slot, n_mtiles, b_tensor, b_slot, b_col0, n_cols, dst, dst_col0, dst_cols, colmap=None, bias=None):
@@ -173,9 +174,10 @@ class RenderNeRF(torch.autograd.Function):
         alpha = torch.empty((R,), **f32)
         depth = torch.empty((R,), **f32) if include_depth else None
         raw = torch.empty((M, 4), **f32)
-        save_h = torch.empty((ns.value, M, 256), dtype=torch.bfloat16, device=device)
+        act_dtype = torch.bfloat16 if eng.operand == "bf16" else torch.float16     # saves are in the operand dtype
+        save_h = torch.empty((ns.value, M, 256), dtype=act_dtype, device=device)
         save_mask = torch.empty((nm.value, M, 8), dtype=torch.int32, device=device)
-        save_enc = torch.empty((2, M, 64), dtype=torch.bfloat16, device=device)
+        save_enc = torch.empty((2, M, 64), dtype=act_dtype, device=device)
         if spec["mode"] == "rays":
             t_vals = torch.empty((R, S), **f32)
             a = spec
@@ -268,7 +270,8 @@ class RenderFFMLP(torch.autograd.Function):
         L = _lib.lib()
         _bind(L)
         device = params[0].device
-        net = _engine.get_engine(model, device).net
+        eng = _engine.get_engine(model, device)
+        net = eng.net
         ns, nm, nd = c_int32(), c_int32(), c_int32()
         _lib._check(L.ffn_train_slots(net.handle, ctypes.byref(ns), ctypes.byref(nm), ctypes.byref(nd)), "ffn_train_slots")
         R, S = spec["R"], spec["S"]
@@ -277,7 +280,8 @@ class RenderFFMLP(torch.autograd.Function):
         color, alpha = torch.empty((R, 3), **f32), torch.empty((R,), **f32)
         depth = torch.empty((R,), **f32) if include_depth else None
         raw = torch.empty((M, 4), **f32)
-        save_h = torch.empty((ns.value, M, 256), dtype=torch.bfloat16, device=device)
+        act_dtype = torch.bfloat16 if eng.operand == "bf16" else torch.float16
+        save_h = torch.empty((ns.value, M, 256), dtype=act_dtype, device=device)
         save_mask = torch.empty((nm.value, M, 8), dtype=torch.int32, device=device)
         if spec["mode"] == "rays":
             t_vals = torch.empty((R, S), **f32)

@@ -131,9 +131,9 @@ struct KernelArgs {
   float* dbg_out;              // (M,256)
   unsigned long long* stats;   // optional [32]: cycle counters (FFN_STATS=1), see ffn_debug_stats
   // training (PASS_TRAIN_FWD writes, PASS_BWD reads masks / writes dz)
-  __nv_bfloat16* save_h;       // [n_save][M][256] layer outputs (bf16, post-activation)
+  __nv_bfloat16* save_h;       // [n_save][M][256] layer outputs, post-activation, in the OPERAND dtype (fp16 | bf16)
   uint32_t* save_mask;         // [n_mask][M][8]   ReLU sign words (bit 31-j of word b <-> column 32b+j is <= 0)
-  __half* save_enc;            // [2][M][64]       position / view encoding rows (our column order), stored as BF16 bits
+  __half* save_enc;            // [2][M][64]       position / view encoding rows (our column order), operand dtype
   const float* d_raw;          // PASS_BWD: (M,4) gradient w.r.t. the raw network outputs [rgb | sigma]
   __nv_bfloat16* dz_out;       // PASS_BWD: [n_dz][M][256] gradients w.r.t. the pre-activations
   int32_t bwd_first_cols;      // PASS_BWD: width of the first dz tile (128 NeRF hidden_view, 256 FourierFeatureMLP)
@@ -144,7 +144,9 @@ struct KernelArgs {
   int32_t num_tiles;
   int32_t lockstep;            // 1: both slots run the same layer and share each weight stage (see kernel)
   int32_t dz_tma;              // PASS_BWD: 1 = dz_out is written by TMA stores of the bf16 A tile (dz_map)
+  int32_t sh_tma;              // PASS_TRAIN_FWD: 1 = save_h is written by TMA stores of the A tile (sh_map)
   alignas(64) CUtensorMap dz_map;   // [n_dz][M][256] bf16, boxes of 64 columns x 32 rows, SWIZZLE_128B
+  alignas(64) CUtensorMap sh_map;   // [n_save][M][256] operand dtype, same boxes
 };
 
 }  // namespace ffn

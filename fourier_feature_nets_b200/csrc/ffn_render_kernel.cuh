@@ -69,13 +69,6 @@ __device__ __forceinline__ float philox_uniform(unsigned long long seed, unsigne
 // columns are permuted to match at pack time):  col 6k+2j = cos(f_k x_j), col 6k+2j+1 =
 // sin(f_k x_j)  (k < 10, j < 3), cols 60..62 = x, col 63 = 0.
 // ----------------------------------------------------------------------------------------
-// packed fp16 pair -> packed bf16 pair (through fp32, round to nearest)
-__device__ __forceinline__ uint32_t half2_to_bf16x2(uint32_t h) {
-  float lo, hi;
-  asm("{\n\t.reg .f16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}" : "=f"(lo), "=f"(hi) : "r"(h));
-  return ptx::pack2<true, false>(lo, hi);
-}
-
 template <bool kBF16>
 __device__ __forceinline__ void write_enc_posenc(uint32_t row_addr, uint32_t row7, float x0,
                                                  float x1, float x2, const float* freq, int nfreq,
@@ -102,17 +95,12 @@ __device__ __forceinline__ void write_enc_posenc(uint32_t row_addr, uint32_t row
   for (uint32_t u = 0; u < 8; ++u)
     ptx::st_shared_v4(row_addr + ((u ^ row7) << 4), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2],
                       pk[4 * u + 3]);
-  if (gsave) {   // training: the 64-wide row as the UMMA reads it (un-swizzled, our column order), always as bf16:
-                 // ffn_wgrad multiplies it with bf16 dz and kind::f16 UMMAs cannot mix fp16 and bf16 operands
+  if (gsave) {   // training: the 64-wide row exactly as the UMMA reads it (un-swizzled, our column order, operand dtype;
+                 // ffn_wgrad converts fp16 rows to bf16 in shared memory)
 #pragma unroll
-    for (uint32_t u = 0; u < 8; ++u) {
-      uint32_t w[4] = {pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]};
-      if constexpr (!kBF16) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) w[e] = half2_to_bf16x2(w[e]);
-      }
-      gsave[u] = make_uint4(w[0], w[1], w[2], w[3]);
-    }
+    for (uint32_t u = 0; u < 8; u += 2)
+      ptx::st_global_v8(gsave + u, pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3], pk[4 * u + 4],
+                        pk[4 * u + 5], pk[4 * u + 6], pk[4 * u + 7]);
   }
 }
 
@@ -183,21 +171,22 @@ __device__ __forceinline__ void store_act_block(const uint32_t (&v)[32], uint32_
   }
 }
 
-// training forward: bf16 copy (post-activation) of 32 columns of one row to HBM as two 32-byte stores; returns the
-// sign word of the accumulator block: bit (31-j) = 1 <=> column j is negative, i.e. ReLU'(.) = 0
-template <bool kRelu, bool kWantMask>
-__device__ __forceinline__ uint32_t save_block_global(const uint32_t (&v)[32], __nv_bfloat16* grow) {
+// 16-bit copy (kBF16: bf16, else fp16; optional ReLU) of 32 columns of one row to HBM as two 32-byte stores
+template <bool kBF16, bool kRelu>
+__device__ __forceinline__ void save_data_global(const uint32_t (&v)[32], void* grow_) {
+  uint16_t* grow = reinterpret_cast<uint16_t*>(grow_);
   uint32_t pk[16];
 #pragma unroll
   for (int q = 0; q < 16; ++q)
-    pk[q] = ptx::pack2<true, kRelu>(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+    pk[q] = ptx::pack2<kBF16, kRelu>(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
   ptx::st_global_v8(grow, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
   ptx::st_global_v8(grow + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+}
+// sign word of an accumulator block: bit (31-j) = 1 <=> column j is negative, i.e. ReLU'(.) = 0
+__device__ __forceinline__ uint32_t sign_word(const uint32_t (&v)[32]) {
   uint32_t w = 0;
-  if constexpr (kWantMask) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) w = __funnelshift_l(v[j], w, 1);
-  }
+  for (int j = 0; j < 32; ++j) w = __funnelshift_l(v[j], w, 1);
   return w;
 }
 
@@ -241,11 +230,13 @@ __device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int b0,
     if constexpr (kPass == PASS_BWD) {
       if constexpr (kMask) apply_sign_mask(v, mwords[b]);
       store_act_block<true, false>(v, chunk_row, row7, u0);
-      if (valid && gh) save_block_global<false, false>(v, gh + b * 32);
+      if (valid && gh) save_data_global<true, false>(v, gh + b * 32);
     } else {
       store_act_block<kBF16, kRelu>(v, chunk_row, row7, u0);
       if constexpr (kPass == PASS_TRAIN_FWD) {
-        if (valid && gh) mwords[b & 7] = save_block_global<kRelu, kRelu>(v, gh + b * 32);
+        // gh == nullptr: the tile leaves through a TMA store of the shared-memory image instead
+        if (valid && gh) save_data_global<kBF16, kRelu>(v, reinterpret_cast<uint16_t*>(gh) + b * 32);
+        if constexpr (kRelu) { if (gm) mwords[b & 7] = sign_word(v); }
       }
     }
   };
@@ -264,7 +255,7 @@ __device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int b0,
   if constexpr (kPass == PASS_TRAIN_FWD && kRelu) {
     // the sign words of this warpgroup's blocks in one store (32 bytes for a 256-wide layer) instead of one
     // 4-byte store per block
-    if (valid && gh && gm) {
+    if (valid && gm) {
       if (nblk == 8)
         ptx::st_global_v8(gm + b0, mwords[0], mwords[1], mwords[2], mwords[3], mwords[4], mwords[5], mwords[6], mwords[7]);
       else
@@ -278,8 +269,9 @@ __device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int b0,
 // nothing is written back.  Fully unrolled so that the head weights are constant-bank operands of the FFMAs
 // (the generic path below indexes them dynamically: an LDC per element, 4x slower); per head the columns are
 // accumulated in ascending order, exactly like the generic path.
-template <int kHn>
-__device__ __forceinline__ void head_layer_epilogue(uint32_t taddr_base, int nblk, float (&hacc)[4]) {
+template <int kHn, bool kSave = false, bool kBF16 = false>
+__device__ __forceinline__ void head_layer_epilogue(uint32_t taddr_base, int nblk, float (&hacc)[4],
+                                                    void* grow = nullptr, uint32_t* gmask = nullptr) {
 #pragma unroll
   for (int i = 0; i < 8; i += 2) {
     if (i < nblk) {
@@ -292,6 +284,17 @@ __device__ __forceinline__ void head_layer_epilogue(uint32_t taddr_base, int nbl
         for (int j = 0; j < 64; ++j)
           a = fmaf(fmaxf(__uint_as_float(v[j]), 0.f), c_params.head_w[o][i * 32 + j], a);
         hacc[o] = a;
+      }
+      if constexpr (kSave) {      // training forward: relu(h) in the operand dtype and the sign words of these 64 columns
+        if (grow) {
+          save_data_global<kBF16, true>(reinterpret_cast<uint32_t(&)[32]>(v[0]), reinterpret_cast<uint16_t*>(grow) + i * 32);
+          save_data_global<kBF16, true>(reinterpret_cast<uint32_t(&)[32]>(v[32]),
+                                        reinterpret_cast<uint16_t*>(grow) + (i + 1) * 32);
+        }
+        if (gmask) {
+          gmask[i] = sign_word(reinterpret_cast<uint32_t(&)[32]>(v[0]));
+          gmask[i + 1] = sign_word(reinterpret_cast<uint32_t(&)[32]>(v[32]));
+        }
       }
     }
   }
@@ -629,6 +632,23 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       ptx::named_bar_sync(bar_id, 128);
       if (eprof) e_back += clock64() - e_t1;
     };
+    // Saves by TMA: every epilogue warp stores its own 32 rows of each 64-column chunk (4 KB boxes) right after its
+    // own fence -- no cross-warp barrier.  (One 128-row box per chunk and tile, issued by one warp behind a
+    // bar.arrive / bar.sync pair, was measured 4 % slower: the passes are bound by HBM write bandwidth, not by
+    // the number of bulk copies.)  Before a warp overwrites its rows, its lane 0 confirms that its stores have
+    // finished reading shared memory.
+    auto tma_tile_free = [&]() {
+      if (lane == 0) ptx::bulk_wait_read_all();
+      __syncwarp();
+    };
+    auto tma_store_tile = [&](const CUtensorMap* map, int nchunks, long long tile_row0, int save_idx) {
+      if (lane == 0) {
+        for (int c = 0; c < nchunks; ++c)
+          ptx::tma_store_3d(map, slot_base + (uint32_t)c * kChunkBytesA + (uint32_t)(wq * 32) * 128u, 64 * c,
+                            (int)tile_row0 + wq * 32, save_idx);
+        ptx::bulk_commit_group();
+      }
+    };
     bool pend = false;                              // a finished tile whose outputs are still to be written
     float p_out[4] = {0.f, 0.f, 0.f, 0.f}, p_tval = 0.f;
     int p_sidx = 0;
@@ -658,10 +678,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
         const int nb0 = args.bwd_first_cols >> 5;
         const uint32_t* mw = args.save_mask + ((size_t)args.bwd_first_mask * args.M + (valid ? row_g : 0)) * 8;
         __nv_bfloat16* gdz = args.dz_out + ((size_t)args.bwd_first_save * args.M + (valid ? row_g : 0)) * 256;
-        if (args.dz_tma) {      // the previous tile's TMA stores must have read this warp's rows of the A tile
-          if (lane == 0) ptx::bulk_wait_read_all();
-          __syncwarp();
-        }
+        if (args.dz_tma) tma_tile_free();      // the previous tile's TMA stores must have read the A tile
         for (int b = 0; b < nb0; ++b) {
           uint32_t v[32];
           const int c0 = b * 32;
@@ -676,7 +693,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           apply_sign_mask(v, valid ? __ldg(mw + b) : 0xffffffffu);
           store_act_block<true, false>(v, slot_base + (uint32_t)(b >> 1) * kChunkBytesA + row_off, row7,
                                        (uint32_t)(b & 1) * 4u);
-          if (valid && !args.dz_tma) save_block_global<false, false>(v, gdz + c0);
+          if (valid && !args.dz_tma) save_data_global<true, false>(v, gdz + c0);
         }
         if (args.bwd_sigma_chunk) {
 #pragma unroll
@@ -747,6 +764,9 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
                                 args.include_inputs != 0, gs);
       } else if (args.enc_kind == ENC_FFMLP) {
         // features [0,128) -> act chunks 0..3, [128,160) -> enc chunk
+        if constexpr (kPass == PASS_TRAIN_FWD) {
+          if (args.sh_tma) tma_tile_free();        // the previous tile's last save may still read chunks 0..3
+        }
         write_enc_ffmlp<kBF16>(slot_base + row_off, row7, px, py, pz, args.ffm_b, args.ffm_a,
                                args.emb, 0, 5);
       } else {
@@ -762,12 +782,8 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
 
       if constexpr (kPass == PASS_BWD) {
         // dz of the first (CUDA-core) layer: this warp's 32 rows of every 64-column chunk, straight from the A tile
-        if (args.dz_tma && grp == 0 && lane == 0) {
-          for (int c = 0; c < (args.bwd_first_cols >> 6); ++c)
-            ptx::tma_store_3d(&args.dz_map, slot_base + (uint32_t)c * kChunkBytesA + (uint32_t)(wq * 32) * 128u, 64 * c,
-                              (int)(tile * kTileM) + wq * 32, args.bwd_first_save);
-          ptx::bulk_commit_group();
-        }
+        if (args.dz_tma && grp == 0)
+          tma_store_tile(&args.dz_map, args.bwd_first_cols >> 6, tile * kTileM, args.bwd_first_save);
       }
       float out[4] = {0.f, 0.f, 0.f, 0.f};  // raw rgb | sigma of this sample
 
@@ -783,6 +799,10 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
         if (eprof) { const long long n = clock64(); e_wait += n - e_t; e_t = n; }
 
         const int blk0 = grp * nblk_grp;
+        bool tile_in_smem = false;     // this layer's output tile sits in the slot's chunks 0.. (TMA-storable)
+        if constexpr (kPass == PASS_TRAIN_FWD) {
+          if (args.sh_tma && grp == 0) tma_tile_free();    // earlier stores have finished reading the tile
+        }
         if (ld.epi == EPI_ENC_PART2) {
           // wide FourierFeatureMLP encodings: features [160, 256) -> act chunks 0..2
           if (grp == 0)
@@ -793,22 +813,27 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
             __nv_bfloat16* gh = (ld.save_idx >= 0 && !args.dz_tma) ? args.dz_out + ((size_t)ld.save_idx * args.M + rg) * 256
                                                                   : nullptr;
             uint32_t* gm = ld.mask_idx >= 0 ? args.save_mask + ((size_t)ld.mask_idx * args.M + rg) * 8 : nullptr;
-            if (args.dz_tma) {      // earlier TMA stores of this warp have finished reading the rows it overwrites now
-              if (lane == 0) ptx::bulk_wait_read_all();
-              __syncwarp();
-            }
+            if (args.dz_tma) tma_tile_free();      // earlier stores have finished reading the tile
             if (ld.epi == EPI_BWD_MASK)
               lean_layer_epilogue<true, false, PASS_BWD, true>(taddr_base, blk0, nblk_grp, slot_base + row_off, row7, gh, gm, valid);
             else
               lean_layer_epilogue<true, false, PASS_BWD, false>(taddr_base, blk0, nblk_grp, slot_base + row_off, row7, gh, gm, valid);
           }
-        } else if (kPass == PASS_INFER && ld.epi == EPI_RELU_HEAD && !ld.sigma_head && args.dbg_layer != l &&
-                   (ld.head_n == 3 || ld.head_n == 4) && (nblk_all & 1) == 0) {
+        } else if ((kPass == PASS_INFER || kPass == PASS_TRAIN_FWD) && ld.epi == EPI_RELU_HEAD && !ld.sigma_head &&
+                   args.dbg_layer != l && (ld.head_n == 3 || ld.head_n == 4) && (nblk_all & 1) == 0) {
           // output heads on CUDA cores, unrolled
           float hacc[4] = {0.f, 0.f, 0.f, 0.f};
           if (grp == 0) {
-            if (ld.head_n == 3) head_layer_epilogue<3>(taddr_base, nblk_all, hacc);
-            else head_layer_epilogue<4>(taddr_base, nblk_all, hacc);
+            if constexpr (kPass == PASS_TRAIN_FWD) {
+              void* gh = (valid && ld.save_idx >= 0) ? args.save_h + ((size_t)ld.save_idx * args.M + row_g) * 256 : nullptr;
+              uint32_t* gm = (valid && ld.mask_idx >= 0) ? args.save_mask + ((size_t)ld.mask_idx * args.M + row_g) * 8
+                                                         : nullptr;
+              if (ld.head_n == 3) head_layer_epilogue<3, true, kBF16>(taddr_base, nblk_all, hacc, gh, gm);
+              else head_layer_epilogue<4, true, kBF16>(taddr_base, nblk_all, hacc, gh, gm);
+            } else {
+              if (ld.head_n == 3) head_layer_epilogue<3>(taddr_base, nblk_all, hacc);
+              else head_layer_epilogue<4>(taddr_base, nblk_all, hacc);
+            }
           }
 #pragma unroll
           for (int o = 0; o < 4; ++o)
@@ -819,9 +844,10 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           __nv_bfloat16* gh = nullptr;
           uint32_t* gm = nullptr;
           if constexpr (kPass == PASS_TRAIN_FWD) {
-            if (ld.save_idx >= 0) gh = args.save_h + ((size_t)ld.save_idx * args.M + rg) * 256;
-            if (ld.mask_idx >= 0) gm = args.save_mask + ((size_t)ld.mask_idx * args.M + rg) * 8;
+            if (ld.save_idx >= 0 && !args.sh_tma) gh = args.save_h + ((size_t)ld.save_idx * args.M + rg) * 256;
+            if (ld.mask_idx >= 0 && !(args.dbg_flags & 16)) gm = args.save_mask + ((size_t)ld.mask_idx * args.M + rg) * 8;
           }
+          tile_in_smem = true;
           if constexpr (kPass != PASS_BWD) {
             constexpr int kP = kPass == PASS_TRAIN_FWD ? PASS_TRAIN_FWD : PASS_INFER;
             float hs = 0.f;
@@ -834,9 +860,10 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           __nv_bfloat16* gh = nullptr;
           uint32_t* gm = nullptr;
           if constexpr (kPass == PASS_TRAIN_FWD) {
-            if (ld.save_idx >= 0) gh = args.save_h + ((size_t)ld.save_idx * args.M + rg) * 256;
-            if (ld.mask_idx >= 0) gm = args.save_mask + ((size_t)ld.mask_idx * args.M + rg) * 8;
+            if (ld.save_idx >= 0 && !args.sh_tma) gh = args.save_h + ((size_t)ld.save_idx * args.M + rg) * 256;
+            if (ld.mask_idx >= 0 && !(args.dbg_flags & 16)) gm = args.save_mask + ((size_t)ld.mask_idx * args.M + rg) * 8;
           }
+          tile_in_smem = true;
           constexpr int kP = kPass == PASS_TRAIN_FWD ? PASS_TRAIN_FWD : PASS_INFER;
           if (ld.epi == EPI_RELU_ACT)
             lean_layer_epilogue<kBF16, true, kP, false>(taddr_base, blk0, nblk_grp, slot_base + row_off, row7, gh, gm, valid);
@@ -846,6 +873,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           // general path: fp32 values are needed (sigma / rgb heads on CUDA cores, debug dump)
           const bool relu = ld.epi != EPI_LINEAR_ACT;
           const bool to_act = ld.epi != EPI_RELU_HEAD;
+          tile_in_smem = to_act;
           float hacc[4] = {0.f, 0.f, 0.f, 0.f};
           const int hn = ld.epi == EPI_RELU_HEAD ? ld.head_n : 0;   // heads 0..hn-1 (rgb | rgb+sigma)
           // output-head layers are converted by the primary warpgroup alone (their fp32 dot products stay in
@@ -885,14 +913,10 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
                 uint32_t* gm = (relu && ld.mask_idx >= 0)
                                    ? args.save_mask + ((size_t)ld.mask_idx * args.M + row_g) * 8 + b : nullptr;
                 // v still holds the raw accumulator (sign source); x holds the activated fp32 values
-                save_block_global<false, false>(reinterpret_cast<uint32_t(&)[32]>(x),
-                                                args.save_h + ((size_t)ld.save_idx * args.M + row_g) * 256 + c0);
-                if (gm) {
-                  uint32_t w = 0;
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) w = __funnelshift_l(v[j], w, 1);
-                  *gm = w;
-                }
+                if (!(args.sh_tma && to_act))
+                  save_data_global<kBF16, false>(reinterpret_cast<uint32_t(&)[32]>(x),
+                                                 args.save_h + ((size_t)ld.save_idx * args.M + row_g) * 256 + c0);
+                if (gm) *gm = sign_word(v);
               }
             }
             if (to_act) {
@@ -931,18 +955,23 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
             else ptx::mbar_arrive(my_a_ready);
           }
         }
+        if constexpr (kPass == PASS_TRAIN_FWD) {
+          // the saved activations of this layer = this warp's 32 rows of the A tile it just wrote, in operand dtype
+          if (args.sh_tma && ld.save_idx >= 0 && tile_in_smem && grp == 0 && !(args.dbg_flags & 32)) {
+            if (l == L - 1) {
+              ptx::fence_proxy_async();
+              __syncwarp();
+            }
+            tma_store_tile(&args.sh_map, ld.n >> 6, tile * kTileM, ld.save_idx);
+          }
+        }
         if constexpr (kPass == PASS_BWD) {
           if (args.dz_tma && ld.save_idx >= 0 && (ld.epi == EPI_BWD_LINEAR || ld.epi == EPI_BWD_MASK)) {
             if (l == L - 1) {      // no UMMA reads the last tile: publish it to the async proxy for the store alone
               ptx::fence_proxy_async();
               __syncwarp();
             }
-            if (lane == 0) {
-              for (int c = 0; c < 4; ++c)
-                ptx::tma_store_3d(&args.dz_map, slot_base + (uint32_t)c * kChunkBytesA + (uint32_t)(wq * 32) * 128u,
-                                  64 * c, (int)(tile * kTileM) + wq * 32, ld.save_idx);
-              ptx::bulk_commit_group();
-            }
+            tma_store_tile(&args.dz_map, 4, tile * kTileM, ld.save_idx);
           }
         }
         if (l == 0 && pend && grp == 0) {
@@ -981,6 +1010,9 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
     if (pend) finish_tile(p_out, p_tval, p_sidx, p_ray, p_row_g, p_valid);
     if constexpr (kPass == PASS_BWD) {
       if (args.dz_tma && lane == 0) ptx::bulk_wait_all();     // the stores source this CTA's shared memory
+    }
+    if constexpr (kPass == PASS_TRAIN_FWD) {
+      if (args.sh_tma && lane == 0) ptx::bulk_wait_all();
     }
     if (eprof) {
       atomicAdd(args.stats + 4, (unsigned long long)e_wait);

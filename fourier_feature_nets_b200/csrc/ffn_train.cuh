@@ -294,6 +294,11 @@ extern "C" int ffn_train_forward(ffn_net_t* net, const float* positions, const f
   ka.raw = raw; ka.save_h = (__nv_bfloat16*)save_h; ka.save_mask = (uint32_t*)save_mask;
   ka.save_enc = (__half*)save_enc;
   fill_train_common(net, ka);
+  // the activations leave the kernel as TMA stores of the A tile (operand dtype); FFN_SH_TMA=0: row-per-thread stores
+  static const bool want_tma = !(getenv("FFN_SH_TMA") && atoi(getenv("FFN_SH_TMA")) == 0);
+  if (want_tma && ka.M < (1ll << 31) - 256 && (reinterpret_cast<uintptr_t>(save_h) & 15) == 0 &&
+      ffn_encode_bf16_3d(&ka.sh_map, save_h, ka.M, 256, net->n_save, 32) == 0)
+    ka.sh_tma = 1;
   const bool fuse = fusable(S);
   ka.fused = fuse ? 1 : 0;
   if (fuse) { ka.rgb = color; ka.alpha = alpha; ka.depth = depth; }

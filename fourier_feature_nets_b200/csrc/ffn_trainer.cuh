@@ -148,7 +148,9 @@ extern "C" int ffn_trainer_backward(ffn_trainer_t* t, const float* positions, co
   if (ffn_train_backward(net, w.d_raw, w.save_mask, M, w.dz, stream_)) return 1;
   // 6. every weight / bias gradient of the MMA layers into the flat buffer
   CUDA_TRY(cudaMemsetAsync(t->flat_grad, 0, (size_t)t->flat_floats * sizeof(float), stream));
-  ffn_wgrad_tensor_t tens[3] = {{w.dz, M, 256, net->n_dz}, {w.save_h, M, 256, net->n_save}, {w.save_enc, M, 64, 2}};
+  const int act_fp16 = net->bf16 ? 0 : 1;      // the forward saves activations / encodings in its operand dtype
+  ffn_wgrad_tensor_t tens[3] = {{w.dz, M, 256, net->n_dz, 0}, {w.save_h, M, 256, net->n_save, act_fp16},
+                                {w.save_enc, M, 64, 2, act_fp16}};
   ffn_wgrad_job_t jobs[ffn::kWgMaxJobs];
   int nj = 0;
   auto job = [&](int a_slot, int n_mt, int b_tensor, int b_slot, int n_cols, int lin, int dst_cols, const int* cm,
@@ -175,10 +177,10 @@ extern "C" int ffn_trainer_backward(ffn_trainer_t* t, const float* positions, co
   const uint8_t* sh = (const uint8_t*)w.save_h;
   const size_t slot = (size_t)M * 256 * 2;
   if (ffn_head_wgrad(w.d_raw, 3, 1, sh + (size_t)(L - 1) * slot, M, t->flat_grad + t->gw_off[L],
-                     t->flat_grad + t->gb_off[L], 256, stream_))
+                     t->flat_grad + t->gb_off[L], 256, act_fp16, stream_))
     return 1;
   if (ffn_head_wgrad(w.d_raw, 0, 3, sh + (size_t)(L + 1) * slot, M, t->flat_grad + t->gw_off[L + 3],
-                     t->flat_grad + t->gb_off[L + 3], 128, stream_))
+                     t->flat_grad + t->gb_off[L + 3], 128, act_fp16, stream_))
     return 1;
   return 0;
 }

@@ -3,9 +3,11 @@
 // of nerf_model.py:111-123 / fourier_feature_models.py:70-77).
 //
 //   A = dz^T   (out x rows)   dz  is [rows][256]  bf16 row-major in HBM  -> "MN-major" UMMA operand
-//   B = x^T    (in  x rows)   x   is [rows][C]    bf16 row-major         -> "MN-major" UMMA operand
-// (kind::f16 UMMAs take fp16 x fp16 or bf16 x bf16, a mixed pair is an illegal instruction on sm_100a: the forward pass
-// therefore saves its encoding rows as bf16)
+//   B = x^T    (in  x rows)   x   is [rows][C]    bf16|fp16 row-major    -> "MN-major" UMMA operand
+// (kind::f16 UMMAs take fp16 x fp16 or bf16 x bf16; a mixed pair is an illegal instruction on sm_100a.  dz needs the
+// bf16 exponent range, the forward saves its activations in its operand dtype -- fp16 by default, as TMA stores of the
+// A tile -- so an fp16 B tile is converted to bf16 IN SHARED MEMORY by the otherwise idle warps 0-3 before the UMMA
+// reads it: 32 KB per stage against ~2700 cycles of HBM time per stage)
 //   D[out][in] += sum_rows dz[row][out] * x[row][in]        fp32 in TMEM
 //
 // The contraction runs over the rows (R*S samples, 65k..131k), so the kernel is a split-K GEMM: a job
@@ -14,7 +16,8 @@
 //   warp 4      TMA producer: 64-row x 64-column boxes (cp.async.bulk.tensor.3d, SWIZZLE_128B) of dz and x straight from
 //               the row-major tensors into a 3-stage ring; rows past the end are zero-filled by the TMA unit
 //   warp 5      TMEM alloc + UMMA issuer: tcgen05.mma kind::f16, M=128, N=n_cols, K=16, both operands MN-major
-//   warps 0-3   while the ring runs: bias gradients (column sums of the dz tile, read from shared memory);
+//   warps 0-3   while the ring runs: fp16 -> bf16 conversion of the B tile (if needed) and bias gradients (column sums
+//               of the dz tile, read from shared memory);
 //               at the end: tcgen05.ld -> red.global.add (v4 where the destination row is 16-byte aligned) straight
 //               into the fp32 gradient tensors in the reference's (out, in) layout, encoding columns un-permuted
 // HBM-bound: every dz / activation byte is read once per job (1 KB per sample row for a 256x256 layer).
@@ -36,6 +39,7 @@ constexpr int kWgSmem = kWgStages * kWgStageBytes + 1024 /*alignment*/ + 256 /*b
 struct WgJob {
   int a_map, a_slot, a_col0, n_mt;       // A: n_mt tiles of 128 dz columns starting at a_col0
   int b_map, b_slot, b_col0, n_cols;     // B: n_cols input columns (multiple of 64, <= 256) starting at b_col0
+  int b_fp16;                            // B tile arrives as fp16: convert to bf16 in shared memory (A is always bf16)
   int dst_stride, dst_col0, dst_cols;    // dW[row][dst_col0 + c], c < dst_cols (or through colmap)
   float* dst;
   const int* colmap;                     // optional: destination column of input column c (< 0: skip)
@@ -75,6 +79,13 @@ __device__ __forceinline__ void wg_wait(uint32_t bar, uint32_t parity) {
     if (spins > (1u << 24)) __trap();
 }
 
+// packed fp16 pair -> packed bf16 pair (through fp32, round to nearest)
+__device__ __forceinline__ uint32_t wg_half2_to_bf16x2(uint32_t h) {
+  float lo, hi;
+  asm("{\n\t.reg .f16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}" : "=f"(lo), "=f"(hi) : "r"(h));
+  return ptx::pack2<true, false>(lo, hi);
+}
+
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -85,9 +96,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) ffn_wgrad_kernel(const __grid_c
   const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* base_ptr = wg_smem_raw + (base - raw);
   const uint32_t bar0 = base + kWgStages * kWgStageBytes;
-  // barriers: full[s] at bar0 + 8 s, empty[s] at bar0 + 64 + 8 s, accumulator-full at bar0 + 128, TMEM address at +136
+  // barriers: full[s] at bar0 + 8 s, empty[s] at bar0 + 64 + 8 s, accumulator-full at bar0 + 128, TMEM address at +136,
+  // converted[s] at bar0 + 192 + 8 s
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 64u + 8u * s; };
+  auto conv_bar = [&](int s) { return bar0 + 192u + 8u * s; };
   const uint32_t acc_bar = bar0 + 128u;
   const uint32_t tmem_slot = bar0 + 136u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + kWgStages * kWgStageBytes + 136);
@@ -97,12 +110,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) ffn_wgrad_kernel(const __grid_c
   const int kt0 = P.cta_kt0[blockIdx.x], kt1 = P.cta_kt1[blockIdx.x];
   const int n_mt = J.n_mt, n_cols = J.n_cols;
   const bool has_bias = J.bias_dst != nullptr;
+  const bool conv = J.b_fp16 != 0;
   const int a_boxes = n_mt * 2, b_boxes = n_cols >> 6;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWgStages; ++s) {
       ptx::mbar_init(full_bar(s), 1);
       ptx::mbar_init(empty_bar(s), has_bias ? 5 : 1);
+      ptx::mbar_init(conv_bar(s), 4);
     }
     ptx::mbar_init(acc_bar, 1);
     ptx::fence_mbar_init();
@@ -143,7 +158,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) ffn_wgrad_kernel(const __grid_c
     int s = 0;
     uint32_t ph = 0;
     for (int kt = kt0; kt < kt1; ++kt) {
-      wg_wait(full_bar(s), ph);
+      wg_wait(conv ? conv_bar(s) : full_bar(s), ph);
       ptx::tc_fence_after();
       if (lane == 0) {
         const uint32_t st = base + (uint32_t)s * kWgStageBytes;
@@ -163,17 +178,31 @@ __global__ void __launch_bounds__(kWgThreads, 1) ffn_wgrad_kernel(const __grid_c
       if (++s == kWgStages) { s = 0; ph ^= 1u; }
     }
   } else {
-    // ------------------------------------------------------------------ warps 0-3: bias sums, then the epilogue
-    if (has_bias) {
+    // ------------------------------------------------------------------ warps 0-3: convert / bias sums, then the epilogue
+    if (has_bias || conv) {
       const int c = 2 * threadIdx.x;                 // this thread's two dz columns
-      const bool active = c < n_mt * 128;
+      const bool active = has_bias && c < n_mt * 128;
       const uint32_t box = (uint32_t)(c >> 6), cc = (uint32_t)(c & 63);
       const uint32_t q = cc >> 3, inner = (cc & 7u) * 2u;
+      const int conv_units = b_boxes * (kWgBoxBytes / 16);      // 16-byte units of the B tile
       float s0 = 0.f, s1 = 0.f;
       int s = 0;
       uint32_t ph = 0;
       for (int kt = kt0; kt < kt1; ++kt) {
         wg_wait(full_bar(s), ph);
+        if (conv) {
+          // element-wise and in place, so the swizzle does not matter
+          const uint32_t bb = base + (uint32_t)s * kWgStageBytes + 4u * kWgBoxBytes;
+          for (int u = threadIdx.x; u < conv_units; u += 128) {
+            uint32_t a0, a1, a2, a3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(bb + 16u * u));
+            ptx::st_shared_v4(bb + 16u * u, wg_half2_to_bf16x2(a0), wg_half2_to_bf16x2(a1), wg_half2_to_bf16x2(a2),
+                              wg_half2_to_bf16x2(a3));
+          }
+          ptx::fence_proxy_async();                  // generic-proxy writes -> visible to the UMMA (async proxy)
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(conv_bar(s));
+        }
         if (active) {
           const uint32_t st = base + (uint32_t)s * kWgStageBytes + box * kWgBoxBytes + inner;
 #pragma unroll 8
@@ -184,8 +213,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) ffn_wgrad_kernel(const __grid_c
             s1 += __uint_as_float(v & 0xffff0000u);
           }
         }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(empty_bar(s));
+        if (has_bias) {
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(empty_bar(s));
+        }
         if (++s == kWgStages) { s = 0; ph ^= 1u; }
       }
       if (active) {
@@ -266,7 +297,7 @@ extern "C" int ffn_wgrad(const ffn_wgrad_tensor_t* tensors, int32_t n_tensors, c
   for (int i = 0; i < n_tensors; ++i) {
     const ffn_wgrad_tensor_t& T = tensors[i];
     if (!T.ptr || T.rows != M || T.cols < 64 || (T.cols & 63) || T.slots < 1 || (reinterpret_cast<uintptr_t>(T.ptr) & 15))
-      return fail("ffn_wgrad: every tensor must be [slots][rows][cols] bf16, cols a multiple of 64, the same rows, "
+      return fail("ffn_wgrad: every tensor must be [slots][rows][cols] 16-bit, cols a multiple of 64, the same rows, "
                   "16-byte aligned");
     const int r = ffn_encode_bf16_3d(&P.maps[i], T.ptr, M, T.cols, T.slots, kWgKTile);
     if (r != 0) return fail("ffn_wgrad: cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
@@ -278,12 +309,13 @@ extern "C" int ffn_wgrad(const ffn_wgrad_tensor_t* tensors, int32_t n_tensors, c
     if (S.a_tensor < 0 || S.a_tensor >= n_tensors || S.b_tensor < 0 || S.b_tensor >= n_tensors || S.n_mtiles < 1 ||
         S.n_mtiles > 2 || S.n_cols < 64 || S.n_cols > 256 || (S.n_cols & 63) || !S.dst ||
         S.a_slot < 0 || S.a_slot >= tensors[S.a_tensor].slots || S.b_slot < 0 || S.b_slot >= tensors[S.b_tensor].slots ||
-        S.a_col0 < 0 || S.a_col0 + 128 * S.n_mtiles > tensors[S.a_tensor].cols || S.b_col0 < 0 ||
+        tensors[S.a_tensor].fp16 || S.a_col0 < 0 || S.a_col0 + 128 * S.n_mtiles > tensors[S.a_tensor].cols || S.b_col0 < 0 ||
         S.b_col0 + S.n_cols > tensors[S.b_tensor].cols || S.dst_cols < 0 || S.dst_cols > S.n_cols)
       return fail("ffn_wgrad: bad job " + std::to_string(j));
     WgJob& J = P.jobs[j];
     J.a_map = S.a_tensor; J.a_slot = S.a_slot; J.a_col0 = S.a_col0; J.n_mt = S.n_mtiles;
     J.b_map = S.b_tensor; J.b_slot = S.b_slot; J.b_col0 = S.b_col0; J.n_cols = S.n_cols;
+    J.b_fp16 = tensors[S.b_tensor].fp16 ? 1 : 0;
     J.dst = S.dst; J.dst_stride = S.dst_stride; J.dst_col0 = S.dst_col0; J.dst_cols = S.dst_cols;
     J.colmap = S.colmap; J.bias_dst = S.bias_dst;
     cost[j] = 128.0 * S.n_mtiles + S.n_cols;

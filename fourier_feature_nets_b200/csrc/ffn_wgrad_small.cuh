@@ -21,12 +21,23 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& v, float (&f)[8]) {
   }
 }
 
+__device__ __forceinline__ void f16x8_to_f32(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 p = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    f[2 * i] = p.x;
+    f[2 * i + 1] = p.y;
+  }
+}
+
 // kHeads = 0: column sums; kHeads = 1..4: kHeads dot products per column with d[m][o0 .. o0 + kHeads)
+// x: (M,256) bf16, or fp16 when x_fp16 (the forward saves activations in its operand dtype)
 template <int kHeads>
 __global__ void __launch_bounds__(kRedThreads)
 rows_reduce_kernel(const __nv_bfloat16* __restrict__ x, long long M, long long slot_stride, const float* __restrict__ d,
                    int o0, float* __restrict__ out, int out_slot_stride, float* __restrict__ dsum, int out_row_stride,
-                   int ncols) {
+                   int ncols, int x_fp16) {
   constexpr int kAcc = kHeads == 0 ? 1 : kHeads;
   __shared__ float red[kRedThreads / 32][kAcc][256 + 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -44,7 +55,8 @@ rows_reduce_kernel(const __nv_bfloat16* __restrict__ x, long long M, long long s
   for (long long m = row0 + warp; m < row1; m += kRedThreads / 32) {
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(xs + m * 256) + lane);
     float f[8];
-    bf16x8_to_f32(v, f);
+    if (x_fp16) f16x8_to_f32(v, f);
+    else bf16x8_to_f32(v, f);
     if constexpr (kHeads == 0) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[0][j] += f[j];
@@ -90,14 +102,14 @@ extern "C" int ffn_colsum_bf16(const void* x, int32_t num_slots, int64_t M, floa
   CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)num_slots * 256 * sizeof(float), stream));
   dim3 grid((unsigned)((M + kRedStrip - 1) / kRedStrip), (unsigned)num_slots);
   rows_reduce_kernel<0><<<grid, kRedThreads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), M,
-                                                          (long long)M * 256, nullptr, 0, out, 256, nullptr, 256, 256);
+                                                          (long long)M * 256, nullptr, 0, out, 256, nullptr, 256, 256, 0);
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
 extern "C" int ffn_head_wgrad(const float* d_raw, int32_t first_head, int32_t num_heads, const void* h, int64_t M,
-                              float* out_w, float* out_b, int32_t num_cols, void* stream_) {
+                              float* out_w, float* out_b, int32_t num_cols, int32_t h_fp16, void* stream_) {
   using namespace ffn;
   if (!d_raw || !h || !out_w || !out_b || first_head < 0 || num_heads < 1 || first_head + num_heads > 4 || M < 0 ||
       num_cols < 1 || num_cols > 256)
@@ -109,10 +121,10 @@ extern "C" int ffn_head_wgrad(const float* d_raw, int32_t first_head, int32_t nu
   dim3 grid((unsigned)((M + kRedStrip - 1) / kRedStrip), 1);
   const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(h);
   switch (num_heads) {
-    case 1: rows_reduce_kernel<1><<<grid, kRedThreads, 0, stream>>>(hp, M, 0, d_raw, first_head, out_w, 0, out_b, num_cols, num_cols); break;
-    case 2: rows_reduce_kernel<2><<<grid, kRedThreads, 0, stream>>>(hp, M, 0, d_raw, first_head, out_w, 0, out_b, num_cols, num_cols); break;
-    case 3: rows_reduce_kernel<3><<<grid, kRedThreads, 0, stream>>>(hp, M, 0, d_raw, first_head, out_w, 0, out_b, num_cols, num_cols); break;
-    default: rows_reduce_kernel<4><<<grid, kRedThreads, 0, stream>>>(hp, M, 0, d_raw, first_head, out_w, 0, out_b, num_cols, num_cols); break;
+    case 1: rows_reduce_kernel<1><<<grid, kRedThreads, 0, stream>>>(hp, M, 0, d_raw, first_head, out_w, 0, out_b, num_cols, num_cols, h_fp16); break;
+    case 2: rows_reduce_kernel<2><<<grid, kRedThreads, 0, stream>>>(hp, M, 0, d_raw, first_head, out_w, 0, out_b, num_cols, num_cols, h_fp16); break;
+    case 3: rows_reduce_kernel<3><<<grid, kRedThreads, 0, stream>>>(hp, M, 0, d_raw, first_head, out_w, 0, out_b, num_cols, num_cols, h_fp16); break;
+    default: rows_reduce_kernel<4><<<grid, kRedThreads, 0, stream>>>(hp, M, 0, d_raw, first_head, out_w, 0, out_b, num_cols, num_cols, h_fp16); break;
   }
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());

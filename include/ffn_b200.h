@@ -168,7 +168,8 @@ int ffn_net_pack_backward(ffn_net_t* net, const float* const* weights, void* str
 
 /* Raycaster.render in training mode: inputs either materialised samples (positions, view_directions,
  * t_values; the ray pointers NULL) or rays (starts, directions, near, far, lin[, jitter]; sample pointers
- * NULL).  Also writes raw (M,4), t_out (R,S) [rays mode], save_h, save_mask, save_enc ([2][M][64] bf16). */
+ * NULL).  Also writes raw (M,4), t_out (R,S) [rays mode], save_h, save_mask, save_enc ([2][M][64]) -- both 16-bit saves in the
+ * operand dtype of the net (fp16 by default, bf16 with FFN_OPERAND_BF16). */
 int ffn_train_forward(ffn_net_t* net, const float* positions, const float* view_directions,
                       const float* t_values, const float* starts, const float* directions,
                       const float* near, const float* far, const float* lin, const float* jitter,
@@ -190,17 +191,19 @@ int ffn_train_backward(ffn_net_t* net, const float* d_raw, const void* save_mask
 int ffn_colsum_bf16(const void* x, int32_t num_slots, int64_t num_points, float* out, void* stream);
 
 /* Gradients of a 1..4-row head evaluated on CUDA cores (opacity_out nerf_model.py:118, color_out :123, final Linear
- * fourier_feature_models.py:77): out_w[o][c] = sum_m d_raw[m][first_head+o] * h[m][c] (h (M,256) bf16, fp32 accumulate),
+ * fourier_feature_models.py:77): out_w[o][c] = sum_m d_raw[m][first_head+o] * h[m][c] (h (M,256) bf16, or fp16 when
+ * h_fp16 is set -- the dtype ffn_train_forward saved it in --, fp32 accumulate),
  * out_b[o] = sum_m d_raw[m][first_head+o];  out_w (num_heads, num_cols) keeps the first num_cols <= 256 columns
  * (color_out reads the 128 hidden_view channels), out_b (num_heads). */
 int ffn_head_wgrad(const float* d_raw, int32_t first_head, int32_t num_heads, const void* h, int64_t num_points,
-                   float* out_w, float* out_b, int32_t num_cols, void* stream);
+                   float* out_w, float* out_b, int32_t num_cols, int32_t h_fp16, void* stream);
 
 /* Weight (and bias) gradients of every MMA layer in ONE launch: dW[out][in] += sum_rows dz[row][out] * x[row][in]
  * (autograd of nn.Linear inside Raycaster.fit, ray_caster.py:319-326; layers nerf_model.py:111-123,
  * fourier_feature_models.py:70-77).  Split-K tcgen05 GEMM over the saved tensors, accumulating with red.global.add
  * into fp32 destinations the CALLER HAS ZEROED.
- *   tensors[i]: [slots][rows][cols] bf16 row-major, cols a multiple of 64, the same
+ *   tensors[i]: [slots][rows][cols] row-major bf16 -- or fp16 when .fp16 is set (B operands only: converted to bf16
+ *               in shared memory; dz, the A operand, must be bf16) --, cols a multiple of 64, the same
  *               `rows` for all, 16-byte aligned.
  *   jobs[j]   : A = n_mtiles (1|2) tiles of 128 columns of slot a_slot of tensors[a_tensor] from a_col0,
  *               B = n_cols (64..256, multiple of 64) columns of slot b_slot of tensors[b_tensor] from b_col0;
@@ -210,7 +213,7 @@ int ffn_head_wgrad(const float* d_raw, int32_t first_head, int32_t num_heads, co
 typedef struct {
   const void* ptr;
   int64_t rows;
-  int32_t cols, slots;
+  int32_t cols, slots, fp16;
 } ffn_wgrad_tensor_t;
 typedef struct {
   int32_t a_tensor, a_slot, a_col0, n_mtiles;

@@ -105,8 +105,34 @@ def test_bad_arguments_fail_loudly():
         _run_wgrad(L, [_wg_tensor(dz), _wg_tensor(x)], [_job(0, 0, 2, 1, 0, 0, 100, dW, 0, 100)])
     with pytest.raises(_lib.FFNError):
         _run_wgrad(L, [_wg_tensor(dz), _wg_tensor(x)], [_job(5, 0, 2, 1, 0, 0, 256, dW, 0, 256)])
-    bad = WgradTensor(x.data_ptr(), 64, 256, 2)      # rows differ from tensor 0
+    bad = WgradTensor(x.data_ptr(), 64, 256, 2, 0)      # rows differ from tensor 0
     ta = (WgradTensor * 2)(_wg_tensor(dz), bad)
     ja = (WgradJob * 1)(_job(0, 0, 2, 1, 0, 0, 256, dW, 0, 256))
     assert L.ffn_wgrad(ta, 2, ja, 1, _lib._stream()) != 0
     assert L.ffn_last_error()
+
+
+@pytest.mark.parametrize("cols", [256, 64])
+def test_fp16_b_operand_is_converted_to_bf16_in_shared_memory(cols):
+    """The forward saves activations in its operand dtype (fp16 by default); ffn_wgrad rounds such a B tile to bf16 in
+    shared memory (kind::f16 UMMAs cannot mix fp16 with the bf16 dz).  Reference: fp32 matmul of dz with the
+    bf16-rounded activations; summation-order tolerance.  Mixed with a bf16 job and a bias in the same launch."""
+    L = _lib.lib()
+    _bind(L)
+    M = 9000
+    dz, xh = _data(M, cols_b=cols, dtype_b=torch.float16, seed=4)
+    _, xb = _data(M, cols_b=256, seed=5)
+    xh[0, :7, :5] = torch.tensor([65504.0, -65504.0, 6e-8, -6e-8, 0.0], device=DEV, dtype=torch.float16)   # range ends
+    dW = torch.zeros((256, cols), device=DEV)
+    dW2 = torch.zeros((256, 256), device=DEV)
+    db = torch.zeros((256,), device=DEV)
+    jobs = [WgradJob(0, 1, 0, 2, 1, 0, 0, cols, dW.data_ptr(), cols, 0, cols, 0, db.data_ptr()),
+            WgradJob(0, 0, 0, 2, 2, 1, 0, 256, dW2.data_ptr(), 256, 0, 256, 0, 0)]
+    _run_wgrad(L, [_wg_tensor(dz), _wg_tensor(xh), _wg_tensor(xb)], jobs)
+    ref = dz[1].float().t() @ xh[0].to(torch.bfloat16).float()
+    assert (dW - ref).abs().max().item() <= _tol(ref, M), ((dW - ref).abs().max().item(), ref.abs().max().item())
+    ref2 = dz[0].float().t() @ xb[1].float()
+    assert (dW2 - ref2).abs().max().item() <= _tol(ref2, M)
+    assert (db - dz[1].float().sum(0)).abs().max().item() <= _tol(ref, M)
+    with pytest.raises(_lib.FFNError):          # dz (the A operand) must be bf16
+        _run_wgrad(L, [_wg_tensor(xh), _wg_tensor(dz)], [WgradJob(0, 0, 0, 2, 1, 0, 0, 256, dW2.data_ptr(), 256, 0, 256, 0, 0)])

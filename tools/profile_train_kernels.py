@@ -40,3 +40,13 @@ for i in range(args.steps):
 e1.record()
 torch.cuda.synchronize()
 print("last step: %.3f ms" % e0.elapsed_time(e1))
+if os.environ.get("FFN_STATS"):
+    # cycle counters of the render-kernel passes (forward-with-saves and dgrad accumulate into the same array)
+    st = trainer.net.debug_stats()
+    tot, wa, ww, n = st[:4]
+    print("epilogue warp 4 (per CTA launch, cycles): wait-acc %.0f  convert+store %.0f  front %.0f  back %.0f" % (
+        st[4] / n, st[5] / n, st[6] / n, st[7] / n))
+    tiles_per_slot = args.steps * R * S / 128 / 2
+    print("epilogue cycles per tile and layer (fwd + bwd summed):", " ".join("%.0f" % (x / tiles_per_slot) for x in st[8:8 + 12]))
+    print("issuer warp: total %.0f cyc/CTA launch, wait-epilogue %.1f%%, wait-weights %.1f%%, issuing %.1f%%" % (
+        tot / n, 100 * wa / tot, 100 * ww / tot, 100 * (tot - wa - ww) / tot))
