@@ -58,8 +58,10 @@ class Raycaster(nn.Module):
                                                     lambda S: self._lin(S, device))
             return RenderResult(color, alpha, depth)
         if not fused:
-            if device.type == "cuda" and not _engine.supported(self.model):
-                raise _lib.FFNError("no libffn_b200 engine for %s" % type(self.model).__name__)
+            if device.type == "cuda" and not needs_grad and not _engine.supported(self.model):
+                # a model family without a fused engine (Voxels, voxels_model.py:35-45, or any nn.Module the caller
+                # brings): its own forward (Voxels: ffn_voxels_forward) + the compositing kernel
+                return self._render_composite_kernel(ray_samples, include_depth)
             return self._render_torch(ray_samples, include_depth)
 
         eng = _engine.get_engine(self.model, device)
@@ -83,11 +85,34 @@ class Raycaster(nn.Module):
     def check_nan(self):
         """Raise like the reference's asserts (ray_caster.py:73-74) if any render since the
         last check produced a NaN colour or opacity.  One device->host read."""
+        flag = self.__dict__.get("_nan_flag")          # models rendered through forward + ffn_composite
+        if flag is not None:
+            v = int(flag.item())
+            if v:
+                flag.zero_()
+            assert not (v & 1), "NaN in rendered colour/opacity"
         eng = self.model.__dict__.get("_ffn_engine")
         if eng is not None:
             flag = eng.net.nan_flag()
             assert not (flag & 0x40000000), "libffn_b200: shared memory base is not 1024-byte aligned"
             assert not (flag & 1), "NaN in rendered colour/opacity"
+
+    def _render_composite_kernel(self, ray_samples: RaySamples, include_depth: bool) -> RenderResult:
+        """model(positions[, views]) followed by ``ffn_composite`` (ray_caster.py:67-93 in one launch)."""
+        if isinstance(ray_samples, RayBundle):
+            ray_samples = ray_samples.materialize()
+        num_rays, num_samples = ray_samples.positions.shape[:2]
+        positions = ray_samples.positions.reshape(-1, 3)
+        if getattr(self.model, "use_view", False):
+            raw = self.model(positions, ray_samples.view_directions.reshape(-1, 3))
+        else:
+            raw = self.model(positions)
+        eng_flag = self.__dict__.setdefault("_nan_flag", torch.zeros(1, dtype=torch.int32, device=raw.device))
+        color, alpha, depth, _ = _lib.composite(raw.reshape(num_rays, num_samples, 4), ray_samples.t_values,
+                                                include_depth, False, eng_flag)
+        if self.check_nan_every_call:
+            assert not (int(eng_flag.item()) & 1), "NaN in rendered colour/opacity"
+        return RenderResult(color, alpha, depth)
 
     def _render_torch(self, ray_samples: RaySamples, include_depth: bool) -> RenderResult:
         """Differentiable definition (ray_caster.py:60-93)."""

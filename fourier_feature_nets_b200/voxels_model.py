@@ -36,7 +36,10 @@ class Voxels(nn.Module):
         if not positions.is_cuda or not self.voxels.is_cuda or needs_grad:
             return self.forward_torch(positions)
         from . import _lib
-        key = (self.voxels._version, self.bias._version, self.voxels.data_ptr())
+        from .engine import _OPT_GENERATION
+        # fused optimisers (ClipAdam, torch's fused Adam) update parameters without bumping the version counters:
+        # any optimiser step since the last copy invalidates it (same rule as engine.Engine.sync_weights)
+        key = (_OPT_GENERATION[0], self.voxels._version, self.bias._version, self.voxels.data_ptr())
         if self._packed is None or self._packed[0] != key:
             self._packed = (key, self.voxels.detach()[0].permute(1, 2, 3, 0).contiguous(),
                             self.bias.detach().reshape(4).tolist())

@@ -345,3 +345,26 @@ def test_fused_trainer_equals_the_autograd_step():
     mat = ffn.RaySamples(mat.positions, mat.view_directions, mat.t_values, torch.arange(50, device=DEV))
     assert torch.isfinite(trainer.backward(mat, gt_c, None, 0.0, torch.linspace(0, 1, 32).to(DEV))).item()
     trainer.update()
+
+
+@pytest.mark.parametrize("preset", ["positional", "gaussian"])
+def test_fit_fourier_feature_mlp_on_the_gpu(tmp_path, preset):
+    """BASELINE.json configs[1] (train_tiny_nerf.py): a FourierFeatureMLP preset through Raycaster.fit on the GPU --
+    training kernels under autograd, fused loss, ClipAdam (the C trainer covers NeRF models only)."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    data = str(tmp_path / "toy.npz")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_synthetic_dataset.py"), data,
+                    "--resolution", "32", "--train", "8", "--val", "2", "--test", "1", "--steps", "64"],
+                   check=True, capture_output=True, timeout=300)
+    train = ffn.ImageDataset.load(data, "train", 64, True, True)
+    val = ffn.ImageDataset.load(data, "val", 64, True, False)
+    torch.manual_seed(0)
+    model = (ffn.PositionalFourierMLP(3, 4, 5.5) if preset == "positional" else ffn.GaussianFourierMLP(3, 4, 3.14)).to(DEV)
+    rc = ffn.Raycaster(model)
+    before = _lib.launch_count()
+    log = rc.fit(train, val, 512, 5e-4, 60, 0, 30, 0.1, 250000, 0, [])
+    assert _lib.launch_count() - before > 300
+    assert train.colors.is_cuda                      # fit moved the tables into HBM
+    assert len(log) >= 2 and log[-1].val_psnr > log[0].val_psnr, [e.val_psnr for e in log]

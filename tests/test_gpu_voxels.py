@@ -119,3 +119,41 @@ def test_focus_sampling_with_a_voxel_opacity_model(S):
         a = rc.render(bundle.to(DEV), True)
         b = rc.render(ref.to(DEV), True)
     assert (a.color - b.color).abs().max().item() <= 5e-3
+
+
+def test_voxels_render_and_fit_on_the_gpu(tmp_path):
+    """train_voxels.py's model on a CUDA device: inference = Voxels.forward (ffn_voxels_forward) + ffn_composite, equal
+    to the PyTorch definition within fp32 rounding (1e-5); training = autograd over grid_sample with the fused loss and
+    ClipAdam, PSNR improves."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    torch.manual_seed(0)
+    model = ffn.Voxels(24, 2.0).to(DEV)
+    with torch.no_grad():
+        model.voxels.normal_(0, 1.5)
+    R, S = 500, 48
+    g = torch.Generator().manual_seed(1)
+    o = torch.tensor([0.1, 0.2, -4.0]).repeat(R, 1)
+    d = torch.nn.functional.normalize(torch.randn((R, 3), generator=g) * 0.12 + torch.tensor([0, 0, 1.0]), dim=-1)
+    near = 2.8 + 0.5 * torch.rand(R, generator=g)
+    bundle = ffn.RayBundle(o, d, near, near + 2.0, torch.arange(R), S, True, torch.rand((R, S), generator=g)).to(DEV)
+    rc = ffn.Raycaster(model.eval())
+    before = _lib.launch_count()
+    with torch.no_grad():
+        out = rc.render(bundle, True)
+        ref = rc._render_torch(bundle.materialize(), True)
+    assert _lib.launch_count() - before >= 2                     # voxel gather + compositing kernels
+    assert (out.color - ref.color).abs().max().item() <= 1e-5 and (out.alpha - ref.alpha).abs().max().item() <= 1e-5
+    assert (out.depth != ref.depth).float().mean().item() <= 0.01
+    rc.check_nan()
+    data = str(tmp_path / "toy.npz")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_synthetic_dataset.py"), data,
+                    "--resolution", "32", "--train", "8", "--val", "2", "--test", "1", "--steps", "64"],
+                   check=True, capture_output=True, timeout=300)
+    train = ffn.ImageDataset.load(data, "train", 32, True, True)
+    val = ffn.ImageDataset.load(data, "val", 32, True, False)
+    model = ffn.Voxels(16, 2 / train.sampler.bounds[0, 0]).to(DEV)
+    log = ffn.Raycaster(model).fit(train, val, 512, 0.01, 40, 0, 20, 0.9, 25000, 0.0, [])
+    assert len(log) >= 2 and log[-1].val_psnr > log[0].val_psnr, [e.val_psnr for e in log]
