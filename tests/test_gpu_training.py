@@ -368,3 +368,29 @@ def test_fit_fourier_feature_mlp_on_the_gpu(tmp_path, preset):
     assert _lib.launch_count() - before > 300
     assert train.colors.is_cuda                      # fit moved the tables into HBM
     assert len(log) >= 2 and log[-1].val_psnr > log[0].val_psnr, [e.val_psnr for e in log]
+
+
+def test_fit_with_hierarchical_sampling_on_the_gpu(tmp_path):
+    """BASELINE.json configs[2] (train_nerf.py with --opacity-model: coarse 64 + fine 128 in the reference): the C
+    trainer on focus-sampled batches -- coarse sigma pass, CDF, inverse transform and sort on the GPU per batch,
+    samples materialised for the forward-with-saves pass."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    data = str(tmp_path / "toy.npz")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_synthetic_dataset.py"), data,
+                    "--resolution", "32", "--train", "8", "--val", "2", "--test", "1", "--steps", "64"],
+                   check=True, capture_output=True, timeout=300)
+    torch.manual_seed(1)
+    coarse = trained_like_model(11).eval()
+    train = ffn.ImageDataset.load(data, "train", 64, True, True, opacity_model=coarse)
+    val = ffn.ImageDataset.load(data, "val", 64, True, False, opacity_model=coarse)
+    assert train.sampler.lazy_focus
+    torch.manual_seed(0)
+    model = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True).to(DEV)
+    rc = ffn.Raycaster(model)
+    before = _lib.launch_count()
+    log = rc.fit(train, val, 512, 5e-4, 40, 0, 20, 0.1, 250000, 0, [])
+    assert _lib.launch_count() - before > 40 * 12
+    assert len(log) >= 2 and log[-1].val_psnr > log[0].val_psnr, [e.val_psnr for e in log]
+    rc.check_nan()
