@@ -20,32 +20,26 @@ class FourierFeatureMLP(nn.Module):
                  a_values: torch.Tensor, b_values: torch.Tensor,
                  layer_channels: List[int]):
         super().__init__()
-        self.params = {
-            "num_inputs": num_inputs,
-            "num_outputs": num_outputs,
-            "a_values": None if a_values is None else a_values.tolist(),
-            "b_values": None if b_values is None else b_values.tolist(),
-            "layer_channels": layer_channels,
-        }
+        encoded = b_values is not None
+        # the constructor arguments, JSON-friendly: ``save`` / ``load_model`` rebuild the model from them
+        self.params = dict(num_inputs=num_inputs, num_outputs=num_outputs,
+                           a_values=a_values.tolist() if a_values is not None else None,
+                           b_values=b_values.tolist() if encoded else None,
+                           layer_channels=layer_channels)
         self.num_inputs = num_inputs
-        if b_values is None:
-            self.a_values = None
-            self.b_values = None
-            width = num_inputs
-        else:
-            assert b_values.shape[0] == num_inputs
-            assert a_values.shape[0] == b_values.shape[1]
-            self.a_values = nn.Parameter(a_values, requires_grad=False)
-            self.b_values = nn.Parameter(b_values, requires_grad=False)
-            width = b_values.shape[1] * 2
-        self.layers = nn.ModuleList()
-        for channels in layer_channels:
-            self.layers.append(nn.Linear(width, channels))
-            width = channels
-        self.layers.append(nn.Linear(width, num_outputs))
         self.use_view = False
         self.keep_activations = False
         self.activations = []
+        if encoded:
+            if b_values.shape[0] != num_inputs or a_values.shape[0] != b_values.shape[1]:
+                raise AssertionError("b_values must be (num_inputs, E) and a_values (E,)")
+            # frozen: they travel with the state dict but are never optimised
+            self.a_values = nn.Parameter(a_values, requires_grad=False)
+            self.b_values = nn.Parameter(b_values, requires_grad=False)
+        else:
+            self.a_values = self.b_values = None
+        widths = [2 * b_values.shape[1] if encoded else num_inputs] + list(layer_channels) + [num_outputs]
+        self.layers = nn.ModuleList(nn.Linear(w_in, w_out) for w_in, w_out in zip(widths, widths[1:]))
 
     def forward_torch(self, inputs: torch.Tensor) -> torch.Tensor:
         if self.b_values is None:
@@ -81,11 +75,15 @@ class FourierFeatureMLP(nn.Module):
         torch.save(state_dict, path)
 
 
+def _hidden(num_layers: int, num_channels: int) -> List[int]:
+    return [num_channels] * num_layers
+
+
 class MLP(FourierFeatureMLP):
     """Un-encoded MLP."""
 
     def __init__(self, num_inputs: int, num_outputs: int, num_layers=3, num_channels=256):
-        super().__init__(num_inputs, num_outputs, None, None, [num_channels] * num_layers)
+        super().__init__(num_inputs, num_outputs, None, None, _hidden(num_layers, num_channels))
 
 
 class BasicFourierMLP(FourierFeatureMLP):
@@ -93,7 +91,7 @@ class BasicFourierMLP(FourierFeatureMLP):
 
     def __init__(self, num_inputs: int, num_outputs: int, num_layers=3, num_channels=256):
         super().__init__(num_inputs, num_outputs, torch.ones(num_inputs), torch.eye(num_inputs),
-                         [num_channels] * num_layers)
+                         _hidden(num_layers, num_channels))
 
 
 class PositionalFourierMLP(FourierFeatureMLP):
@@ -101,9 +99,8 @@ class PositionalFourierMLP(FourierFeatureMLP):
 
     def __init__(self, num_inputs: int, num_outputs: int, max_log_scale: float,
                  num_layers=3, num_channels=256, embedding_size=256):
-        b_values = self._encoding(max_log_scale, embedding_size, num_inputs)
-        super().__init__(num_inputs, num_outputs, torch.ones(b_values.shape[1]), b_values,
-                         [num_channels] * num_layers)
+        freqs = self._encoding(max_log_scale, embedding_size, num_inputs)
+        super().__init__(num_inputs, num_outputs, torch.ones(freqs.shape[1]), freqs, _hidden(num_layers, num_channels))
 
     @staticmethod
     def _encoding(max_log_scale: float, embedding_size: int, num_inputs: int):
@@ -115,6 +112,5 @@ class GaussianFourierMLP(FourierFeatureMLP):
 
     def __init__(self, num_inputs: int, num_outputs: int, sigma: float,
                  num_layers=3, num_channels=256, embedding_size=256):
-        b_values = torch.normal(0, sigma, size=(num_inputs, embedding_size))
-        super().__init__(num_inputs, num_outputs, torch.ones(b_values.shape[1]), b_values,
-                         [num_channels] * num_layers)
+        freqs = torch.normal(0, sigma, size=(num_inputs, embedding_size))
+        super().__init__(num_inputs, num_outputs, torch.ones(embedding_size), freqs, _hidden(num_layers, num_channels))
