@@ -364,3 +364,29 @@ def test_no_undefined_names_in_the_package():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_names.py")] + files,
                          capture_output=True, text=True)
     assert res.returncode == 0, res.stdout
+
+
+def test_orbit_video_frames_shard_over_two_ranks_gloo(tmp_path):
+    """tools/orbit_video_multi_gpu.py (configs[4]: orbit frames split over the ranks, no data-path collective): two gloo
+    ranks on the CPU write exactly the frames a single process writes, pixel for pixel."""
+    torch.manual_seed(3)
+    model = ffn.NeRF(2, 32, 3, 4, 2, 2, [1], True)
+    path = str(tmp_path / "m.pt")
+    model.save(path)
+    tool = os.path.join(ROOT, "tools", "orbit_video_multi_gpu.py")
+    common = [path, "12", "--num-frames", "5", "--num-samples", "8", "--device", "cpu", "--batch_size", "64"]
+    one, two = str(tmp_path / "one"), str(tmp_path / "two")
+    res = subprocess.run([sys.executable, tool, common[0], common[1], one] + common[2:], capture_output=True, text=True,
+                         timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29641", tool, common[0], common[1], two] + common[2:]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert '"n_ranks": 2' in res.stdout
+    import cv2
+    names = sorted(os.listdir(one))
+    assert names == ["frame_%05d.png" % i for i in range(5)] == sorted(os.listdir(two))
+    for n in names:
+        assert np.array_equal(cv2.imread(os.path.join(one, n)), cv2.imread(os.path.join(two, n))), n
