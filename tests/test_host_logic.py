@@ -390,3 +390,30 @@ def test_orbit_video_frames_shard_over_two_ranks_gloo(tmp_path):
     assert names == ["frame_%05d.png" % i for i in range(5)] == sorted(os.listdir(two))
     for n in names:
         assert np.array_equal(cv2.imread(os.path.join(one, n)), cv2.imread(os.path.join(two, n))), n
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every prototype of include/ffn_b200.h is exported, listed in EXPORTED_SYMBOLS, and -- where the Python binding
+    declares ``argtypes`` -- bound with the same number of parameters (a drifted signature would otherwise only show
+    up as garbage arguments on the GPU box)."""
+    import re
+    from fourier_feature_nets_b200 import autograd, optim, trainer
+    hdr = open(os.path.join(ROOT, "include", "ffn_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|void|int64_t|const char\*)\s+(ffn_\w+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    assert len(protos) >= 35
+    assert set(protos) == set(_lib.EXPORTED_SYMBOLS), set(protos) ^ set(_lib.EXPORTED_SYMBOLS)
+    L = _lib.lib()
+    autograd._bind(L)
+    optim._bind(L)
+    trainer._bind(L)
+    checked = 0
+    for name, n in protos.items():
+        fn = getattr(L, name)
+        if fn.argtypes is not None:
+            assert len(fn.argtypes) == n, (name, len(fn.argtypes), n)
+            checked += 1
+    assert checked >= 15, checked
