@@ -12,6 +12,7 @@ from .image_dataset import ImageDataset, RayDataset
 from .nerf_model import NeRF
 from .optim import ClipAdam
 from .pixel_dataset import PixelData, PixelDataset
+from .signal_dataset import SignalData, SignalDataset
 from .ray_caster import Raycaster
 from .trainer import FusedTrainer
 from .ray_dataset_modes import Mode
@@ -30,4 +31,4 @@ __all__ = ["CameraInfo", "Resolution", "MLP", "NeRF", "BasicFourierMLP", "Fourie
            "PositionalFourierMLP", "GaussianFourierMLP", "Raycaster", "RayCaster", "RaySampler",
            "RaySamples", "RayBundle", "FocusBundle", "RenderResult", "Mode", "ImageDataset", "RayDataset", "calculate_blend_weights",
            "exponential_lr_decay", "linspace", "load_model", "orbit", "ETABar", "EvaluationVisualizer",
-           "OrbitVideoVisualizer", "ActivationVisualizer", "ComparisonVisualizer", "Voxels", "ClipAdam", "FusedTrainer", "PixelDataset", "PixelData", "__version__"]
+           "OrbitVideoVisualizer", "ActivationVisualizer", "ComparisonVisualizer", "Voxels", "ClipAdam", "FusedTrainer", "PixelDataset", "PixelData", "SignalDataset", "SignalData", "__version__"]

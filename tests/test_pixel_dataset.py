@@ -66,3 +66,13 @@ def test_activation_mosaic_shape(tmp_path):
     model = ffn.BasicFourierMLP(2, 3, num_channels=64)
     img = ds.to_act_image(model, 64)
     assert img.shape == (64, 64, 3) and img.dtype == np.uint8 and not model.keep_activations
+
+
+def test_signal_dataset_create():
+    """signal_dataset.py:39-67: x = linspace(0, 2, n * rate, endpoint=False) float32, every rate-th point trains."""
+    ds = ffn.SignalDataset.create(lambda x: np.sin(3 * np.pi * x), 16, 8)
+    assert ds.val_x.shape == (128, 1) and ds.train_x.shape == (16, 1) and ds.val_x.dtype == torch.float32
+    assert np.array_equal(ds.train_x.numpy(), ds.val_x.numpy()[::8]) and np.array_equal(ds.train_y.numpy(), ds.val_y.numpy()[::8])
+    assert ds.val_x[0, 0].item() == 0.0 and abs(ds.val_x[-1, 0].item() - (2 - 2 / 128)) < 1e-6
+    lo, hi = ds.x_lim
+    assert lo < 0 < 2 - 2 / 128 < hi and abs((hi - lo) - 1.1 * (2 - 2 / 128)) < 1e-5
