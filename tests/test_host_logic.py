@@ -417,3 +417,19 @@ def test_ctypes_signatures_match_the_header():
             assert len(fn.argtypes) == n, (name, len(fn.argtypes), n)
             checked += 1
     assert checked >= 15, checked
+
+
+def test_cuda_only_training_components_refuse_cpu_models():
+    """ClipAdam and FusedTrainer have no CPU implementation (Raycaster.fit uses the reference's PyTorch calls on a CPU
+    model): they fail loudly instead of falling back."""
+    model = ffn.NeRF(2, 32, 3, 4, 2, 2, [1], True)
+    with pytest.raises(_lib.FFNError):
+        ffn.FusedTrainer(model, 5e-4)
+    opt = ffn.ClipAdam(model.parameters(), 5e-4)
+    for p in model.parameters():
+        if p.requires_grad:
+            p.grad = torch.zeros_like(p)
+    with pytest.raises(_lib.FFNError):
+        opt.step()
+    with pytest.raises(ValueError):            # one parameter group only: the norm is clipped over all of them
+        ffn.ClipAdam([{"params": [model.layers[0].weight]}, {"params": [model.layers[0].bias]}], 5e-4)
