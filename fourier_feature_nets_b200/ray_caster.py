@@ -245,7 +245,7 @@ class Raycaster(nn.Module):
                 if step > num_steps:
                     break
                 exponential_lr_decay(optim, learning_rate, step, decay_rate, decay_steps)
-                batch = index[start:min(start + batch_size, num_rays)].tolist()
+                batch = index[start:min(start + batch_size, num_rays)]       # numpy slice (the reference makes a list)
                 if trainer is not None:
                     rays = train_dataset.get_rays(batch, step).to(device)
                     if len(rays.rays) > 0:      # (an all-background batch is a NaN loss in the reference)

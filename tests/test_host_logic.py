@@ -433,3 +433,23 @@ def test_cuda_only_training_components_refuse_cpu_models():
         opt.step()
     with pytest.raises(ValueError):            # one parameter group only: the norm is clipped over all of them
         ffn.ClipAdam([{"params": [model.layers[0].weight]}, {"params": [model.layers[0].bias]}], 5e-4)
+
+
+def test_bench_reference_arm_runs_on_the_cpu_and_keeps_the_contract():
+    """``bench.py --impl reference`` (the driver's reference arm) needs no GPU and nothing of the product package:
+    one JSON line with the base contract's keys; the product arm refuses to run without a GPU."""
+    import json
+    bench = os.path.join(ROOT, "bench.py")
+    res = subprocess.run([sys.executable, bench, "--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-rays",
+                          "512"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "rays/s" and line["value"] > 0
+    assert line["metric"].startswith("rays/sec (lego_400, 64 samples/ray)") and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["rays_per_step"] == 512 and line["steps"] == 1
+    if not torch.cuda.is_available():
+        res = subprocess.run([sys.executable, bench, "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                             timeout=600)
+        assert res.returncode != 0 and "needs a GPU" in (res.stdout + res.stderr)
