@@ -115,7 +115,7 @@ EXPORTED_SYMBOLS = [
     "ffn_train_slots", "ffn_net_pack_backward", "ffn_train_forward", "ffn_composite_backward",
     "ffn_train_backward", "ffn_colsum_bf16", "ffn_head_wgrad", "ffn_wgrad", "ffn_clip_adam", "ffn_mse_loss",
     "ffn_trainer_create", "ffn_trainer_destroy", "ffn_trainer_workspace_bytes", "ffn_trainer_backward",
-    "ffn_trainer_update",
+    "ffn_trainer_update", "ffn_trainer_set_grad_scale",
 ]
 
 
@@ -299,7 +299,7 @@ class Net:
         return color, alpha, depth, t_out
 
     def focus_sample(self, starts, directions, near, far, near_u, far_u, lin_c, lin_u, jitter_u, u_focus,
-                     stratified: bool, seed: int, num_samples: int) -> torch.Tensor:
+                     stratified: bool, seed: int, num_samples: int, ray_offset: int = 0) -> torch.Tensor:
         """coarse sigma pass of THIS net + inverse-transform sampling -> sorted t (R, num_samples)."""
         o, d = _f32c(starts, "starts"), _f32c(directions, "directions")
         nr, fr = _f32c(near, "near"), _f32c(far, "far")
@@ -312,7 +312,7 @@ class Net:
         with on_device(self.device):
             _check(lib().ffn_focus_sample(self.handle, _ptr(o), _ptr(d), _ptr(nr), _ptr(fr), _ptr(nu), _ptr(fu),
                                           _ptr(lc), _ptr(lu), _ptr(lc), _ptr(ju), _ptr(uf), int(bool(stratified)),
-                                          c_uint64(seed & (2**64 - 1)), 0, R, num_samples, _ptr(t), _stream()),
+                                          c_uint64(seed & (2**64 - 1)), ray_offset, R, num_samples, _ptr(t), _stream()),
                    "ffn_focus_sample")
         return t
 
@@ -402,7 +402,7 @@ def voxels_forward(grid_channels_last: torch.Tensor, bias4, scale: float, positi
 
 
 def focus_t(raw_sigma: torch.Tensor, near, far, near_u, far_u, lin_c, lin_u, jitter_u, u_focus,
-            stratified: bool, seed: int, num_samples: int) -> torch.Tensor:
+            stratified: bool, seed: int, num_samples: int, ray_offset: int = 0) -> torch.Tensor:
     """``ffn_focus_t`` on given coarse opacity logits (R, S_c) or raw outputs (R, S_c, 4)."""
     raw = _f32c(raw_sigma, "raw")
     stride = 4 if raw.dim() == 3 else 1
@@ -414,6 +414,6 @@ def focus_t(raw_sigma: torch.Tensor, near, far, near_u, far_u, lin_c, lin_u, jit
         _check(lib().ffn_focus_t(_ptr(raw), stride, _ptr(_f32c(near, "near")), _ptr(_f32c(far, "far")),
                                  _ptr(_f32c(near_u, "near_u")), _ptr(_f32c(far_u, "far_u")), _ptr(_f32c(lin_c, "lin_c")),
                                  _ptr(_f32c(lin_u, "lin_u")), _ptr(_f32c(lin_c, "lin_c")), _ptr(ju), _ptr(uf),
-                                 int(bool(stratified)), c_uint64(seed & (2**64 - 1)), 0, R, num_samples, _ptr(t),
+                                 int(bool(stratified)), c_uint64(seed & (2**64 - 1)), ray_offset, R, num_samples, _ptr(t),
                                  _stream()), "ffn_focus_t")
     return t

@@ -24,6 +24,7 @@ struct OptArgs {
   int first_block[kOptMaxTensors + 1];          // prefix sums of ceil(numel / kOptChunk)
   int n;
   float clip_value, max_norm, lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2;
+  float grad_scale;                             // gradients are multiplied by this first (1 / world size: the mean of an all-reduced sum)
   float* norm_sq;                               // [0] total (written by block 0 of clip_adam_kernel), [1 + b] partials
   int n_blocks;
 };
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(kOptThreads) clip_sumsq_kernel(const __grid_co
   for (int i = 0; i < 8; ++i) {
     const long long e = base + threadIdx.x + (long long)i * kOptThreads;
     if (e < a.numel[t]) {
-      float v = g[e];
+      float v = g[e] * a.grad_scale;
       if (c > 0.f) v = fminf(fmaxf(v, -c), c);
       s = fmaf(v, v, s);
     }
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(kOptThreads) clip_adam_kernel(const __grid_con
   for (int i = 0; i < 8; ++i) {
     const long long e = base + threadIdx.x + (long long)i * kOptThreads;
     if (e < a.numel[t]) {
-      float gv = g[e];
+      float gv = g[e] * a.grad_scale;
       if (c > 0.f) gv = fminf(fmaxf(gv, -c), c);
       gv *= coef;
       g[e] = gv;
@@ -113,9 +114,9 @@ __global__ void __launch_bounds__(kOptThreads) clip_adam_kernel(const __grid_con
 
 }  // namespace ffn
 
-extern "C" int ffn_clip_adam(const ffn_adam_tensor_t* tensors, int32_t n, float clip_value, float max_norm, float lr,
-                             float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
-                             float bias_correction2, float* norm_sq, int32_t norm_scratch_floats, void* stream_) {
+static int clip_adam_scaled(const ffn_adam_tensor_t* tensors, int32_t n, float grad_scale, float clip_value, float max_norm,
+                            float lr, float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
+                            float bias_correction2, float* norm_sq, int32_t norm_scratch_floats, void* stream_) {
   using namespace ffn;
   if (n == 0) return 0;
   if (!tensors || n < 0 || n > kOptMaxTensors || !norm_sq || !(bias_correction1 > 0.f) || !(bias_correction2 > 0.f))
@@ -137,6 +138,7 @@ extern "C" int ffn_clip_adam(const ffn_adam_tensor_t* tensors, int32_t n, float 
   a.clip_value = clip_value; a.max_norm = max_norm; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
   a.weight_decay = weight_decay; a.bias_correction1 = bias_correction1; a.bias_correction2 = bias_correction2;
   a.norm_sq = norm_sq;
+  a.grad_scale = grad_scale;
   a.n_blocks = blocks;
   if (blocks + 1 > norm_scratch_floats) return fail("ffn_clip_adam: norm scratch too small");
   clip_sumsq_kernel<<<blocks, kOptThreads, 0, stream>>>(a);
@@ -144,4 +146,11 @@ extern "C" int ffn_clip_adam(const ffn_adam_tensor_t* tensors, int32_t n, float 
   g_launches += 2;
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+extern "C" int ffn_clip_adam(const ffn_adam_tensor_t* tensors, int32_t n, float clip_value, float max_norm, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
+                             float bias_correction2, float* norm_sq, int32_t norm_scratch_floats, void* stream_) {
+  return clip_adam_scaled(tensors, n, 1.f, clip_value, max_norm, lr, beta1, beta2, eps, weight_decay, bias_correction1,
+                          bias_correction2, norm_sq, norm_scratch_floats, stream_);
 }

@@ -20,6 +20,9 @@ struct ffn_trainer {
   float* exp_avg = nullptr;
   float* exp_avg_sq = nullptr;
   int64_t flat_floats = 0;
+  cudaStream_t side = nullptr;           // the two CUDA-core head reductions run here, beside dgrad + wgrad
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  float grad_scale = 1.f;                // ffn_trainer_set_grad_scale: 1 / world size after a summing all-reduce
   int* d_colmaps = nullptr;              // 3 x 64: pos encoding -> cols [0..), pos -> [256..), view -> [256..)
 };
 
@@ -56,6 +59,8 @@ extern "C" int64_t ffn_trainer_workspace_bytes(const ffn_net_t* net, int64_t num
   if (!net || !net->trainable || num_rays < 0 || num_samples < 1) return -1;
   return (int64_t)trainer_carve(net, nullptr, num_rays, num_samples).bytes;
 }
+
+extern "C" void ffn_trainer_destroy(ffn_trainer_t* t);
 
 extern "C" int ffn_trainer_create(ffn_net_t* net, const ffn_trainer_desc_t* d, ffn_trainer_t** out) {
   if (!net || !d || !out) return fail("ffn_trainer_create: null argument");
@@ -107,12 +112,21 @@ extern "C" int ffn_trainer_create(ffn_net_t* net, const ffn_trainer_desc_t* d, f
     delete t;
     return fail("ffn_trainer_create: cudaMalloc/cudaMemcpy of the column maps failed");
   }
+  if (cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    ffn_trainer_destroy(t);
+    return fail("ffn_trainer_create: stream / event creation failed");
+  }
   *out = t;
   return 0;
 }
 
 extern "C" void ffn_trainer_destroy(ffn_trainer_t* t) {
   if (!t) return;
+  if (t->ev_fork) cudaEventDestroy(t->ev_fork);
+  if (t->ev_join) cudaEventDestroy(t->ev_join);
+  if (t->side) cudaStreamDestroy(t->side);
   if (t->d_colmaps) cudaFree(t->d_colmaps);
   delete t;
 }
@@ -144,10 +158,27 @@ extern "C" int ffn_trainer_backward(ffn_trainer_t* t, const float* positions, co
     return 1;
   // 3. compositing backward, 4. transposed weight images, 5. dgrad chain
   if (ffn_composite_backward(w.raw, tv, R, S, w.g_color, gt_alphas ? w.g_alpha : nullptr, w.d_raw, stream_)) return 1;
+  CUDA_TRY(cudaMemsetAsync(t->flat_grad, 0, (size_t)t->flat_floats * sizeof(float), stream));
+  // 3b. the CUDA-core heads need only d_raw and saved activations: they run on a side stream beside the dgrad chain
+  // and ffn_wgrad (disjoint ranges of the flat buffer) and join before this call returns.
+  // opacity_out reads trunk output L-1, color_out the 128 hidden_view channels (slot L+1)
+  {
+    const int act16 = net->bf16 ? 0 : 1;
+    const uint8_t* sh = (const uint8_t*)w.save_h;
+    const size_t slot = (size_t)M * 256 * 2;
+    CUDA_TRY(cudaEventRecord(t->ev_fork, stream));
+    CUDA_TRY(cudaStreamWaitEvent(t->side, t->ev_fork, 0));
+    if (ffn_head_wgrad(w.d_raw, 3, 1, sh + (size_t)(L - 1) * slot, M, t->flat_grad + t->gw_off[L],
+                       t->flat_grad + t->gb_off[L], 256, act16, t->side))
+      return 1;
+    if (ffn_head_wgrad(w.d_raw, 0, 3, sh + (size_t)(L + 1) * slot, M, t->flat_grad + t->gw_off[L + 3],
+                       t->flat_grad + t->gb_off[L + 3], 128, act16, t->side))
+      return 1;
+    CUDA_TRY(cudaEventRecord(t->ev_join, t->side));
+  }
   if (ffn_net_pack_backward(net, t->w.data(), stream_)) return 1;
   if (ffn_train_backward(net, w.d_raw, w.save_mask, M, w.dz, stream_)) return 1;
   // 6. every weight / bias gradient of the MMA layers into the flat buffer
-  CUDA_TRY(cudaMemsetAsync(t->flat_grad, 0, (size_t)t->flat_floats * sizeof(float), stream));
   const int act_fp16 = net->bf16 ? 0 : 1;      // the forward saves activations / encodings in its operand dtype
   ffn_wgrad_tensor_t tens[3] = {{w.dz, M, 256, net->n_dz, 0}, {w.save_h, M, 256, net->n_save, act_fp16},
                                 {w.save_enc, M, 64, 2, act_fp16}};
@@ -173,15 +204,13 @@ extern "C" int ffn_trainer_backward(ffn_trainer_t* t, const float* positions, co
   job(L + 1, 1, 1, L, 256, L + 2, 256, nullptr, true);                 // hidden_view (nerf_model.py:121-122)
   job(L + 1, 1, 2, 1, 64, L + 2, 64, t->d_colmaps + 128, false);
   if (ffn_wgrad(tens, 3, jobs, nj, stream_)) return 1;
-  // 7. the CUDA-core heads: opacity_out reads trunk output L-1, color_out the 128 hidden_view channels (slot L+1)
-  const uint8_t* sh = (const uint8_t*)w.save_h;
-  const size_t slot = (size_t)M * 256 * 2;
-  if (ffn_head_wgrad(w.d_raw, 3, 1, sh + (size_t)(L - 1) * slot, M, t->flat_grad + t->gw_off[L],
-                     t->flat_grad + t->gb_off[L], 256, act_fp16, stream_))
-    return 1;
-  if (ffn_head_wgrad(w.d_raw, 0, 3, sh + (size_t)(L + 1) * slot, M, t->flat_grad + t->gw_off[L + 3],
-                     t->flat_grad + t->gb_off[L + 3], 128, act_fp16, stream_))
-    return 1;
+  CUDA_TRY(cudaStreamWaitEvent(stream, t->ev_join, 0));      // 7. join the head reductions
+  return 0;
+}
+
+extern "C" int ffn_trainer_set_grad_scale(ffn_trainer_t* t, float grad_scale) {
+  if (!t || !(grad_scale > 0.f)) return fail("ffn_trainer_set_grad_scale: bad argument");
+  t->grad_scale = grad_scale;
   return 0;
 }
 
@@ -194,8 +223,8 @@ extern "C" int ffn_trainer_update(ffn_trainer_t* t, float clip_value, float max_
     ts.push_back({t->w[i], t->flat_grad + t->gw_off[i], t->exp_avg + t->gw_off[i], t->exp_avg_sq + t->gw_off[i], t->w_numel[i]});
     ts.push_back({t->b[i], t->flat_grad + t->gb_off[i], t->exp_avg + t->gb_off[i], t->exp_avg_sq + t->gb_off[i], t->b_numel[i]});
   }
-  if (ffn_clip_adam(ts.data(), (int32_t)ts.size(), clip_value, max_norm, lr, beta1, beta2, eps, weight_decay,
-                    bias_correction1, bias_correction2, norm_scratch, norm_scratch_floats, stream_))
+  if (clip_adam_scaled(ts.data(), (int32_t)ts.size(), t->grad_scale, clip_value, max_norm, lr, beta1, beta2, eps,
+                       weight_decay, bias_correction1, bias_correction2, norm_scratch, norm_scratch_floats, stream_))
     return 1;
   return ffn_net_pack(t->net, t->w.data(), t->b.data(), stream_);
 }

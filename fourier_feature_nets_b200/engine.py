@@ -6,6 +6,7 @@ optimiser step costs two small kernel launches and no host synchronisation.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -26,14 +27,72 @@ def _linear_list(model) -> List[torch.nn.Linear]:
     raise _lib.FFNError("model type %s has no libffn_b200 engine" % type(model).__name__)
 
 
+def unsupported_reason(model) -> Optional[str]:
+    """``None`` if the fused sm_100a kernels cover this model (kind AND shape), else why not.
+
+    The kernels are specialised for the BASELINE configurations: 256-wide trunks (one 128x256 fp32 TMEM
+    accumulator per tile), <= 10 frequencies per encoding (a 64-wide encoding chunk), 3-D inputs, 4 outputs."""
+    kind = getattr(model, "_ffn_kind", None)
+    if kind == "nerf":
+        p = model.params
+        if p["num_channels"] != 256:
+            return "num_channels = %d (the kernels are built for 256)" % p["num_channels"]
+        if not 1 <= p["num_layers"] <= 10:
+            return "num_layers = %d (1..10)" % p["num_layers"]
+        if not (0 <= p["num_freq_pos"] <= _lib.FFN_MAX_FREQS and 0 <= p["num_freq_view"] <= _lib.FFN_MAX_FREQS):
+            return "more than %d frequencies per encoding" % _lib.FFN_MAX_FREQS
+        if 0 in set(p["skips"]):
+            return "a skip connection into layer 0"
+        if 6 * p["num_freq_pos"] + (3 if p["include_inputs"] else 0) < 1:
+            return "empty positional encoding"
+        return None
+    if kind == "fourier":
+        if model.keep_activations:
+            return "keep_activations is set (the fused kernels keep hidden activations on chip)"
+        if not model._engine_ok():
+            return "only 3 -> [256] * n -> 4 FourierFeatureMLPs with embedding size <= 256 are covered"
+        return None
+    return "model type %s has no libffn_b200 engine" % type(model).__name__
+
+
 def supported(model) -> bool:
-    return getattr(model, "_ffn_kind", None) in ("nerf", "fourier")
+    """Kind and shape are covered by the fused kernels."""
+    return unsupported_reason(model) is None
+
+
+def note_unfused(model):
+    """A NeRF / FourierFeatureMLP on a CUDA device whose SHAPE the fused kernels do not cover is evaluated by its
+    plain PyTorch definition (the reference supports arbitrary widths; compositing still runs in ``ffn_composite``).
+    Never silently: a ``UserWarning`` once per model, or an ``FFNError`` when ``FFN_STRICT=1``."""
+    if getattr(model, "_ffn_kind", None) not in ("nerf", "fourier") or model.__dict__.get("_ffn_unfused_noted"):
+        return
+    why = unsupported_reason(model)
+    if why is None or why.startswith("keep_activations"):
+        return
+    msg = ("libffn_b200: %s is outside the fused sm_100a kernels (%s); its layers run as plain PyTorch ops"
+           % (type(model).__name__, why))
+    if os.environ.get("FFN_STRICT", "0") not in ("", "0"):
+        raise _lib.FFNError(msg + " and FFN_STRICT is set")
+    import warnings
+    warnings.warn(msg, UserWarning, stacklevel=3)
+    model.__dict__["_ffn_unfused_noted"] = True
+
+
+def _encoding_signature(model) -> Tuple:
+    """(storage pointer, version) of the frozen encoding buffers: they are baked into the C handle at creation, so
+    ``load_state_dict`` of a checkpoint with another B matrix / other frequencies must rebuild the handle."""
+    if model._ffn_kind == "nerf":
+        bufs = (model.pos_encoding, model.view_encoding)
+    else:
+        bufs = (model.a_values, model.b_values)
+    return tuple((None, None) if b is None else (b.data_ptr(), b._version) for b in bufs)
 
 
 class Engine:
     def __init__(self, model, device: torch.device, operand: str):
         self.device = device
         self.operand = operand
+        self.enc_sig = _encoding_signature(model)
         kind = model._ffn_kind
         if kind == "nerf":
             p = model.params
@@ -86,7 +145,7 @@ def mark_weights_changed():
 def get_engine(model, device: torch.device, operand: Optional[str] = None) -> Engine:
     operand = operand or getattr(model, "ffn_operand", DEFAULT_OPERAND)
     eng = model.__dict__.get("_ffn_engine")
-    if eng is None or eng.device != device or eng.operand != operand:
+    if eng is None or eng.device != device or eng.operand != operand or eng.enc_sig != _encoding_signature(model):
         eng = Engine(model, device, operand)
         model.__dict__["_ffn_engine"] = eng
     eng.sync_weights(model)

@@ -84,7 +84,7 @@ class NeRF(nn.Module):
 
     def forward(self, position: torch.Tensor, view: torch.Tensor) -> torch.Tensor:
         """(N,3) positions, (N,3) unit view directions -> (N,4) [rgb_raw | sigma_raw]."""
-        if position.is_cuda and not _needs_grad(self, position, view):
+        if position.is_cuda and not _needs_grad(self, position, view) and _engine.supported(self):
             eng = _engine.get_engine(self, position.device)
             return eng.net.mlp_forward(position.reshape(-1, 3), view.reshape(-1, 3))
         return self.forward_torch(position, view)

@@ -50,7 +50,11 @@ def allreduce_gradients(model: torch.nn.Module, average: bool = True):
         base = flat.untyped_storage().data_ptr()
         if all(g.untyped_storage().data_ptr() == base for g in grads):
             dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-            if average:
+            trainer = model.__dict__.get("_ffn_trainer")
+            if trainer is not None and trainer.flat_grad is flat:
+                # FusedTrainer: the mean is taken inside ffn_clip_adam (g * 1/ws before clipping), no extra launch
+                trainer.set_grad_scale(1.0 / ws if average else 1.0)
+            elif average:
                 flat /= ws
             return
     flat = torch.cat([g.reshape(-1) for g in grads])

@@ -46,10 +46,11 @@ class Raycaster(nn.Module):
         """Render the ray samples -> per-ray colour (R,3), alpha (R), depth (R)."""
         device = next(self.model.parameters()).device
         needs_grad = _needs_grad(self.model)
-        fused = device.type == "cuda" and _engine.supported(self.model) and not needs_grad
-        kind = getattr(self.model, "_ffn_kind", None)
-        trainable = kind == "nerf" or (kind == "fourier" and self.model._engine_ok() and not self.model.keep_activations)
-        if device.type == "cuda" and needs_grad and trainable and self.train_kernels:
+        eng_ok = device.type == "cuda" and _engine.supported(self.model)      # kind AND shape
+        fused = eng_ok and not needs_grad
+        if device.type == "cuda" and not eng_ok:
+            _engine.note_unfused(self.model)       # warns once (FFN_STRICT=1: raises); Voxels etc. are silent
+        if needs_grad and eng_ok and self.train_kernels:
             from .autograd import render_nerf_train
             if isinstance(ray_samples, FocusBundle):     # t values come from the (frozen) coarse model
                 with torch.no_grad():
@@ -58,7 +59,7 @@ class Raycaster(nn.Module):
                                                     lambda S: self._lin(S, device))
             return RenderResult(color, alpha, depth)
         if not fused:
-            if device.type == "cuda" and not needs_grad and not _engine.supported(self.model):
+            if device.type == "cuda" and not needs_grad and not eng_ok:
                 # a model family without a fused engine (Voxels, voxels_model.py:35-45, or any nn.Module the caller
                 # brings): its own forward (Voxels: ffn_voxels_forward) + the compositing kernel
                 return self._render_composite_kernel(ray_samples, include_depth)
@@ -73,7 +74,7 @@ class Raycaster(nn.Module):
             b = ray_samples
             color, alpha, depth, _ = eng.net.render_rays(
                 b.starts, b.directions, b.near, b.far, self._lin(b.num_samples, device), b.jitter,
-                b.stratified, b.seed, 0, b.num_samples, include_depth)
+                b.stratified, b.seed, b.ray_offset, b.num_samples, include_depth)
         else:
             views = ray_samples.view_directions if self.model.use_view else None
             color, alpha, depth = eng.net.render_samples(ray_samples.positions, views,
@@ -269,6 +270,9 @@ class Raycaster(nn.Module):
                     epoch += 1
                     train_psnr = self._validate(trainval, batch_size, step)
                     val_psnr = self._validate(val_dataset, batch_size, step)
+                    # the reference asserts "no NaN colour / opacity" on every render (ray_caster.py:73-74); the
+                    # kernels raise a device flag instead, read here where the loop synchronises anyway
+                    self.check_nan()
                     now = time.time()
                     if step >= report_interval:
                         time_per_step = (now - start_time) / step

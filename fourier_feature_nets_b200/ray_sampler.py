@@ -52,7 +52,8 @@ class RayBundle(RaySamples):
     """
 
     def __new__(cls, starts, directions, near, far, rays, num_samples: int,
-                stratified: bool = False, jitter: Optional[torch.Tensor] = None, seed: int = 0):
+                stratified: bool = False, jitter: Optional[torch.Tensor] = None, seed: int = 0,
+                ray_offset: int = 0):
         self = super().__new__(cls, None, None, None, rays)
         self.starts = starts
         self.directions = directions
@@ -62,6 +63,10 @@ class RayBundle(RaySamples):
         self.stratified = bool(stratified)
         self.jitter = jitter
         self.seed = int(seed)
+        # position of ray 0 of this bundle inside the bundle ``sample()`` returned: in-kernel jitter is
+        # Philox(seed, ray_offset + i, sample), so the sub-batches of ``batched_render`` draw independent jitter
+        self.ray_offset = int(ray_offset)
+        self._stage = None          # pinned staging set these tensors live in (RaySampler.enable_pinned_staging)
         self._cache = None
         return self
 
@@ -76,7 +81,7 @@ class RayBundle(RaySamples):
             if self.stratified:
                 jitter = self.jitter
                 if jitter is None:
-                    gen = torch.Generator(device=self.near.device).manual_seed(self.seed)
+                    gen = torch.Generator(device=self.near.device).manual_seed(self.seed + 7919 * self.ray_offset)
                     jitter = torch.rand((len(self.near), S), dtype=torch.float32,
                                         device=self.near.device, generator=gen)
                 scale = (self.far - self.near) / S
@@ -99,23 +104,40 @@ class RayBundle(RaySamples):
         return self.materialize()[i]
 
     # ---- RaySamples API, staying compact ----------------------------------------------
-    def _map(self, fn) -> "RayBundle":
+    def _map(self, fn, ray_offset: Optional[int] = None) -> "RayBundle":
         return RayBundle(fn(self.starts), fn(self.directions), fn(self.near), fn(self.far),
                          None if self.rays is None else fn(self.rays), self.num_samples,
-                         self.stratified, None if self.jitter is None else fn(self.jitter), self.seed)
+                         self.stratified, None if self.jitter is None else fn(self.jitter), self.seed,
+                         self.ray_offset if ray_offset is None else ray_offset)
 
     def to(self, *args, **kwargs) -> "RayBundle":
-        return self._map(lambda t: t.to(*args, **kwargs))
+        out = self._map(lambda t: t.to(*args, **kwargs))
+        if self._stage is not None and out.starts.is_cuda:
+            # the copies out of the pinned staging set are in flight on the current stream: sample() waits for this
+            # event before it overwrites the set
+            self._stage.event = torch.cuda.Event()
+            self._stage.event.record()
+        return out
 
     def pin_memory(self) -> "RayBundle":
+        if self._stage is not None:         # already lives in pinned memory
+            return self
         return self._map(lambda t: t.pin_memory())
 
-    def subset(self, index) -> "RayBundle":
+    def _subset_offset(self, index):
+        """(index, ray_offset of the subset): contiguous ranges become slices and keep their position; a gather
+        gets a hashed offset so that its in-kernel jitter differs from the parent's."""
         if isinstance(index, (list, range)) and len(index) > 0:
             lo, hi = index[0], index[-1] + 1
             if hi - lo == len(index):         # contiguous: a view, not a gather
-                index = slice(lo, hi)
-        return self._map(lambda t: t[index])
+                return slice(lo, hi), self.ray_offset + lo
+        if isinstance(index, slice):
+            return index, self.ray_offset + (index.start or 0)
+        return index, self.ray_offset
+
+    def subset(self, index) -> "RayBundle":
+        index, off = self._subset_offset(index)
+        return self._map(lambda t: t[index], off)
 
     def numpy(self) -> RaySamples:
         return self.materialize().numpy()
@@ -150,7 +172,7 @@ class FocusBundle(RayBundle):
             eng = _engine.get_engine(model, dev)
             return eng.net.focus_sample(self.starts, self.directions, self.near_raw, self.far_raw, self.near,
                                         self.far, lin_c, lin_u, self.jitter, self.u_focus, self.stratified,
-                                        self.seed, S)
+                                        self.seed, S, self.ray_offset)
         # any other opacity model on the device (e.g. ``Voxels``): its own forward gives the coarse raw outputs at
         # t_c = linspace(near, far, S_c) (ray_sampler.py:246-263), the CDF / inverse transform / sort run in
         # ``ffn_focus_t``
@@ -165,7 +187,8 @@ class FocusBundle(RayBundle):
             else:
                 raw = model(pos)
         return _lib.focus_t(raw.reshape(n, n_f, -1)[..., -1].contiguous(), self.near_raw, self.far_raw, self.near,
-                            self.far, lin_c, lin_u, self.jitter, self.u_focus, self.stratified, self.seed, S)
+                            self.far, lin_c, lin_u, self.jitter, self.u_focus, self.stratified, self.seed, S,
+                            self.ray_offset)
 
     def materialize(self) -> RaySamples:
         if self._cache is None:
@@ -176,11 +199,13 @@ class FocusBundle(RayBundle):
             self._cache = RaySamples(pos, dirs, t, tuple.__getitem__(self, 3))
         return self._cache
 
-    def _map(self, fn) -> "FocusBundle":
-        return FocusBundle(fn(self.starts), fn(self.directions), fn(self.near), fn(self.far), fn(self.near_raw),
-                           fn(self.far_raw), None if self.rays is None else fn(self.rays), self.num_samples,
-                           self.stratified, None if self.jitter is None else fn(self.jitter),
-                           None if self.u_focus is None else fn(self.u_focus), self.seed, self.coarse_model)
+    def _map(self, fn, ray_offset: Optional[int] = None) -> "FocusBundle":
+        out = FocusBundle(fn(self.starts), fn(self.directions), fn(self.near), fn(self.far), fn(self.near_raw),
+                          fn(self.far_raw), None if self.rays is None else fn(self.rays), self.num_samples,
+                          self.stratified, None if self.jitter is None else fn(self.jitter),
+                          None if self.u_focus is None else fn(self.u_focus), self.seed, self.coarse_model)
+        out.ray_offset = self.ray_offset if ray_offset is None else ray_offset
+        return out
 
 
 def _determine_cdf(t_values: torch.Tensor, opacity: torch.Tensor) -> torch.Tensor:
@@ -273,6 +298,38 @@ class RaySampler:
                 t = linspace(self.near_far[0, sl], self.near_far[1, sl], num_focus)
                 cdfs.append(_determine_cdf(t, self._determine_opacity(t, self.starts[sl], self.directions[sl])))
             self.cdfs = torch.cat(cdfs)
+
+    # ---- host tables: pinned staging ---------------------------------------------------------
+    def enable_pinned_staging(self, max_rays: int, depth: int = 2) -> "RaySampler":
+        """Host-resident ray tables: ``sample()`` gathers each batch (<= ``max_rays`` rays) straight into one of
+        ``depth`` rotating sets of page-locked buffers, so ``bundle.to(device, non_blocking=True)`` is an async DMA
+        and no pinned memory is allocated per call.  A set is rewritten only after the copies out of it have
+        finished (event recorded by ``RayBundle.to``)."""
+        class _Set:
+            def __init__(self, n):
+                self.starts = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+                self.directions = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+                self.near = torch.empty((n,), dtype=torch.float32).pin_memory()
+                self.far = torch.empty((n,), dtype=torch.float32).pin_memory()
+                self.rays = torch.empty((n,), dtype=torch.int64).pin_memory()
+                self.event = None
+        self._stage_sets = [_Set(int(max_rays)) for _ in range(depth)]
+        self._stage_next = 0
+        return self
+
+    def _stage_gather(self, idx: torch.Tensor):
+        st = self._stage_sets[self._stage_next]
+        self._stage_next = (self._stage_next + 1) % len(self._stage_sets)
+        if st.event is not None:
+            st.event.synchronize()
+            st.event = None
+        n = len(idx)
+        torch.index_select(self.starts, 0, idx, out=st.starts[:n])
+        torch.index_select(self.directions, 0, idx, out=st.directions[:n])
+        torch.index_select(self.near_far[0], 0, idx, out=st.near[:n])
+        torch.index_select(self.near_far[1], 0, idx, out=st.far[:n])
+        st.rays[:n].copy_(idx)
+        return st, st.starts[:n], st.directions[:n], st.near[:n], st.far[:n], st.rays[:n]
 
     # ---- device residency (section 8f-1): keep the ray tables in HBM ----------------------
     def to(self, device) -> "RaySampler":
@@ -392,9 +449,14 @@ class RaySampler:
             idx = torch.as_tensor(idx, dtype=torch.long)
         idx_dev = idx.to(self.device)
         n = len(idx_dev)
-        starts = self.starts[idx_dev]
-        directions = self.directions[idx_dev]
-        near, far = self.near_far[:, idx_dev]
+        stage = None
+        if (getattr(self, "_stage_sets", None) and not self.starts.is_cuda and not self.focus_sampling
+                and n <= len(self._stage_sets[0].near)):
+            stage, starts, directions, near, far, idx_dev = self._stage_gather(idx_dev)
+        else:
+            starts = self.starts[idx_dev]
+            directions = self.directions[idx_dev]
+            near, far = self.near_far[:, idx_dev]
         if step is not None and step < self.num_anneal_steps:
             anneal = min(max(step / self.num_anneal_steps, self.anneal_start), 1)
             mid = (near + far) * 0.5
@@ -408,8 +470,10 @@ class RaySampler:
                 # host path keeps the reference's RNG stream (ray_sampler.py:383)
                 jitter = torch.rand((n, self.num_samples), dtype=torch.float32)
             self._draws += 1
-            return RayBundle(starts, directions, near, far, idx_dev, self.num_samples,
-                             self.stratified, jitter, self.seed + self._draws)
+            bundle = RayBundle(starts, directions, near, far, idx_dev, self.num_samples,
+                               self.stratified, jitter, self.seed + self._draws)
+            bundle._stage = stage
+            return bundle
 
         if self.lazy_focus:
             near_raw, far_raw = self.near_far[:, idx_dev]

@@ -40,11 +40,12 @@ def _bind(L):
                                                                      c_void_p, c_void_p, c_float, c_void_p, c_int64,
                                                                      c_void_p, c_void_p, c_void_p]
     L.ffn_trainer_update.argtypes = [c_void_p] + [c_float] * 9 + [c_void_p, c_int32, c_void_p]
+    L.ffn_trainer_set_grad_scale.argtypes = [c_void_p, c_float]
     L._trainer_bound = True
 
 
 def supported(model) -> bool:
-    if getattr(model, "_ffn_kind", None) != "nerf":
+    if getattr(model, "_ffn_kind", None) != "nerf" or not _engine.supported(model):
         return False
     params = [q for lin in _engine._linear_list(model) for q in (lin.weight, lin.bias)]
     return all(q.is_cuda and q.dtype == torch.float32 and q.is_contiguous() and q.requires_grad for q in params)
@@ -80,6 +81,8 @@ class FusedTrainer:
         for prm, v in zip(params, views):
             prm.grad = v                                   # persistent: every step rewrites the same memory
         model.__dict__["_ffn_flat_grad"] = self.flat_grad  # parallel.allreduce_gradients reduces it in place
+        model.__dict__["_ffn_trainer"] = self              # ... and folds the 1 / world size into the update
+        self.grad_scale = 1.0
         n = len(lins)
         self._w = (c_void_p * n)(*[lin.weight.data_ptr() for lin in lins])
         self._b = (c_void_p * n)(*[lin.bias.data_ptr() for lin in lins])
@@ -164,6 +167,13 @@ class FusedTrainer:
                 self.handle, g["clip_value"], g["max_norm"], g["lr"], beta1, beta2, g["eps"], g["weight_decay"],
                 1.0 - beta1 ** self.step_count, 1.0 - beta2 ** self.step_count, _lib._ptr(self._norm),
                 self._norm.numel(), _lib._stream()), "ffn_trainer_update")
+
+    def set_grad_scale(self, scale: float):
+        """Multiply every gradient by ``scale`` inside the update kernels (``1 / world_size`` after a summing
+        all-reduce): the mean of the data-parallel gradients without another pass over the buffer."""
+        if scale != self.grad_scale:
+            _lib._check(self._L.ffn_trainer_set_grad_scale(self.handle, float(scale)), "ffn_trainer_set_grad_scale")
+            self.grad_scale = float(scale)
 
     def total_norm(self) -> float:
         return math.sqrt(float(self._norm[0].item()))

@@ -71,7 +71,8 @@ def load_model(path: str) -> torch.nn.Module:
             print("Unable to find model", path, "(no network: assets cannot be downloaded)")
             return None
         path = alt
-    state = torch.load(path, map_location="cpu", weights_only=False)
+    # tensors + a "type" string + a "params" dict of lists / numbers: loads under the safe unpickler
+    state = torch.load(path, map_location="cpu", weights_only=True)
     kind, params = state.pop("type"), state.pop("params")
     if kind == "fourier":
         for key in ("a_values", "b_values"):

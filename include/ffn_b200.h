@@ -282,6 +282,10 @@ int ffn_trainer_backward(ffn_trainer_t* trainer, const float* positions, const f
                          int64_t num_rays, int32_t num_samples, const float* gt_colors, const float* gt_alphas,
                          const int64_t* rays, float alpha_weight, void* workspace, int64_t workspace_bytes, float* loss,
                          int32_t* nan_flag, void* stream);
+/* Data-parallel training: the flat gradient buffer holds the SUM over `1 / grad_scale` ranks after the all-reduce;
+ * ffn_trainer_update multiplies every gradient by grad_scale (default 1) before clipping, i.e. the mean costs no
+ * extra pass over the buffer.  The reference is single-device (ray_caster.py:319-329 has no counterpart). */
+int ffn_trainer_set_grad_scale(ffn_trainer_t* trainer, float grad_scale);
 /* ffn_clip_adam over all parameters + ffn_net_pack */
 int ffn_trainer_update(ffn_trainer_t* trainer, float clip_value, float max_norm, float lr, float beta1, float beta2,
                        float eps, float weight_decay, float bias_correction1, float bias_correction2,

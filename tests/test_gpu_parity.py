@@ -320,7 +320,7 @@ def test_full_size_properties(golden_nerf):
     sl = slice(12345, 12345 + 777)
     cs, as_, ds = run(sl)
     assert torch.equal(cs, c[sl]) and torch.equal(as_, a[sl])
-    eng.net.nan_flag() == 0
+    assert eng.net.nan_flag() == 0
 
 
 @pytest.mark.parametrize("env", [{"FFN_USE_TS": "1"}, {"FFN_PAIR": "0", "FFN_LOCKSTEP": "1"}, {"FFN_PAIR": "0"}])

@@ -441,14 +441,22 @@ def test_bench_reference_arm_runs_on_the_cpu_and_keeps_the_contract():
     import json
     bench = os.path.join(ROOT, "bench.py")
     res = subprocess.run([sys.executable, bench, "--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-rays",
-                          "512"], capture_output=True, text=True, timeout=600)
+                          "512"], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, OMP_NUM_THREADS="1"))      # what torchrun exports at N > 1
     assert res.returncode == 0, res.stdout + res.stderr
     line = json.loads(res.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "rays/s" and line["value"] > 0
     assert line["metric"].startswith("rays/sec (lego_400, 64 samples/ray)") and line["higher_is_better"] is True
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    from oracle import reference as refmod
+    assert line["cpu_baseline"]["kind"] == ("reference" if refmod.available() else "port")
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))      # not torchrun's OMP_NUM_THREADS=1
+    assert "512 rays" in line["cpu_baseline"]["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert line["config"]["rays_per_step"] == 512 and line["steps"] == 1
+    # the config is the product arm's config (the sample is described in cpu_baseline.sample)
+    import bench as bench_mod
+    ns = type("A", (), dict(rays=1 << 20, steps=1, warmup=1))
+    assert line["config"] == bench_mod.bench_config(ns, 1) and line["steps"] == 1
+    assert len(res.stdout.strip().splitlines()) == 1          # nothing but the JSON line on stdout
     if not torch.cuda.is_available():
         res = subprocess.run([sys.executable, bench, "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
                              timeout=600)
