@@ -349,3 +349,51 @@ assert err <= 2.5e-3 and mis <= 0.02
     res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True,
                          timeout=300)
     assert res.returncode == 0 and "ERR" in res.stdout, res.stdout[-1000:] + res.stderr[-2000:]
+
+
+def test_engine_follows_changed_encoding_buffers():
+    """a GaussianFourierMLP that has already rendered on CUDA and then receives ``load_state_dict``
+    of a checkpoint with ANOTHER B matrix must render with the new B (the encoding buffers are baked into the C
+    handle: the engine signature covers them and the handle is rebuilt)."""
+    torch.manual_seed(1)
+    m = ffn.GaussianFourierMLP(3, 4, 3.0).to(DEV).eval()
+    x = torch.rand((4096, 3), device=DEV) * 2 - 1
+    with torch.no_grad():
+        first = m(x)
+        torch.manual_seed(2)
+        other = ffn.GaussianFourierMLP(3, 4, 5.0)
+        m.load_state_dict(other.state_dict())
+        got = m(x)
+        want = m.forward_torch(x)
+    assert not torch.allclose(first, got, atol=1e-2)
+    assert (got - want).abs().max() <= 4e-3 * want.abs().max().clamp_min(1.0)
+    # NeRF: other frequencies through load_state_dict
+    n1 = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True).to(DEV).eval()
+    v = torch.nn.functional.normalize(torch.randn((4096, 3), device=DEV), dim=-1)
+    with torch.no_grad():
+        n1(x, v)
+        sd = ffn.NeRF(8, 256, 6, 10, 2, 4, [4], True).state_dict()
+        n1.load_state_dict(sd)
+        got, want = n1(x, v), n1.forward_torch(x, v)
+    assert (got - want).abs().max() <= 4e-3 * want.abs().max().clamp_min(1.0)
+
+
+def test_batched_render_draws_independent_jitter_per_batch():
+    """in-kernel stratified jitter is Philox(seed, ray_offset + i, sample); the sub-batches of
+    ``batched_render`` must not repeat the jitter of batch 0 (the reference draws torch.rand per ray)."""
+    torch.manual_seed(3)
+    m = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True)
+    with torch.no_grad():
+        m.opacity_out.bias += 3.0            # visible density, so that jitter moves the pixels
+    m = m.to(DEV).eval()
+    n = 512
+    o = torch.tensor([0.1, 0.2, -4.0], device=DEV).repeat(2 * n, 1)
+    d = torch.nn.functional.normalize(torch.tensor([0.02, -0.03, 1.0], device=DEV), dim=0).repeat(2 * n, 1)
+    near, far = torch.full((2 * n,), 3.0, device=DEV), torch.full((2 * n,), 5.0, device=DEV)
+    b = ffn.RayBundle(o, d, near, far, torch.arange(2 * n, device=DEV), 64, True, None, seed=11)
+    rc = ffn.Raycaster(m)
+    whole = rc.batched_render(b, 2 * n, False).color
+    halves = rc.batched_render(b, n, False).color
+    np.testing.assert_array_equal(whole, halves)               # batching does not change the draws ...
+    assert np.abs(halves[:n] - halves[n:]).max() > 1e-4         # ... and identical rays in different batches differ
+    assert np.abs(halves[0] - halves[1]).max() > 1e-5

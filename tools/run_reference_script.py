@@ -11,6 +11,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 script = os.path.abspath(sys.argv[1])
+if not os.path.exists(script):      # a bare script name: the copy vendored next to the oracle (GPU box) or the checkout
+    for base in (os.path.join(ROOT, "oracle", "_ref"), os.environ.get("FFN_REFERENCE", "/root/reference")):
+        if os.path.exists(os.path.join(base, sys.argv[1])):
+            script = os.path.join(base, sys.argv[1])
+            break
 sys.argv = [script] + sys.argv[2:]
 sys.path = [os.path.join(ROOT, "compat"), ROOT] + [p for p in sys.path
                                                      if os.path.abspath(p or ".") != os.path.dirname(script)]
@@ -19,6 +24,14 @@ if not os.environ.get("DISPLAY"):
     import cv2
     cv2.imshow = lambda *a, **k: None
     cv2.waitKey = lambda *a, **k: -1
+if os.environ.get("FFN_REPORT_LAUNCHES"):
+    # tests: prove that the script's work went through libffn_b200 (kernel launches issued by the library)
+    import atexit
+
+    def _report():
+        from fourier_feature_nets_b200 import _lib
+        print("FFN_LAUNCHES", _lib.launch_count() if _lib._lib is not None else 0)
+    atexit.register(_report)
 code = compile(open(script).read(), script, "exec")
 globs = {"__name__": "__main__", "__file__": script}
 exec(code, globs)
