@@ -60,6 +60,20 @@ def exponential_lr_decay(optim: torch.optim.Optimizer, initial_learning_rate: fl
         group["lr"] = lr
 
 
+def _safe_load(path: str):
+    allow = [np.dtype, np.ndarray]
+    for mod in ("numpy._core.multiarray", "numpy.core.multiarray"):
+        try:
+            m = __import__(mod, fromlist=["scalar"])
+            allow += [m.scalar, m._reconstruct]
+            break
+        except (ImportError, AttributeError):
+            continue
+    allow += [type(np.dtype(t)) for t in (np.float32, np.float64, np.int32, np.int64, np.bool_)]
+    with torch.serialization.safe_globals(allow):
+        return torch.load(path, map_location="cpu", weights_only=True)
+
+
 def load_model(path: str) -> torch.nn.Module:
     """Load a ``.pt`` written by ``model.save`` (reference format: state dict + "type" +
     "params", utils.py:448-503) and return it in eval mode."""
@@ -71,8 +85,10 @@ def load_model(path: str) -> torch.nn.Module:
             print("Unable to find model", path, "(no network: assets cannot be downloaded)")
             return None
         path = alt
-    # tensors + a "type" string + a "params" dict of lists / numbers: loads under the safe unpickler
-    state = torch.load(path, map_location="cpu", weights_only=True)
+    # tensors + a "type" string + a "params" dict of lists / numbers: loads under the safe unpickler.  Checkpoints
+    # written by the reference may carry numpy scalars in "params" (train_voxels.py:99-101): allow exactly the numpy
+    # scalar / dtype reconstructors, nothing else
+    state = _safe_load(path)
     kind, params = state.pop("type"), state.pop("params")
     if kind == "fourier":
         for key in ("a_values", "b_values"):

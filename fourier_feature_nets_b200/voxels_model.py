@@ -12,6 +12,9 @@ class Voxels(nn.Module):
 
     def __init__(self, side: int, scale: float):
         nn.Module.__init__(self)
+        # plain Python numbers (train_voxels.py:99-101 passes a numpy scalar for ``scale``): the checkpoint then loads
+        # under torch's safe unpickler
+        side, scale = int(side), float(scale)
         self.params = {"side": side, "scale": scale}
         self.voxels = nn.Parameter(torch.zeros((1, 4, side, side, side), dtype=torch.float32))
         bias = torch.zeros(4, dtype=torch.float32)
