@@ -13,7 +13,6 @@
 #include "ffn_tma_host.cuh"
 #include "ffn_common.cuh"
 #include "ffn_render_kernel.cuh"
-#include "ffn_render_ts_kernel.cuh"
 
 using namespace ffn;
 
@@ -93,19 +92,9 @@ struct ffn_net {
   size_t wpack_bwd_bytes = 0;
   int n_save = 0, n_mask = 0, n_dz = 0;
   int bwd_first_cols = 0, bwd_first_heads = 0, bwd_first_mask = 0, bwd_first_save = 0, bwd_sigma_chunk = 0;
-  // v3 ("TS") inference kernel: N-half-major weight images
-  bool ts_ready = false;
-  TsLayer layers_ts[kMaxMmaLayers];
-  uint8_t* d_wpack_ts = nullptr;
-  size_t wpack_ts_bytes = 0;
-  uint32_t ts_off[kMaxMmaLayers], ts_half_bytes[kMaxMmaLayers], ts_bias_half[kMaxMmaLayers];
 };
 static int build_nerf_backward(ffn_net* net, int L);
 static int build_ffmlp_backward(ffn_net* net, int H);
-static int build_ts_program(ffn_net* net);
-struct PackArgs;
-static int pack_ts(ffn_net* net, const PackArgs& pa, cudaStream_t stream);
-static int launch_ts(ffn_net* net, const KernelArgs& ka, cudaStream_t stream);
 
 static std::atomic<long long> g_gen{1};
 static long long g_loaded_gen = 0;   // generation currently resident in c_params
@@ -437,7 +426,7 @@ extern "C" int ffn_nerf_create(const ffn_nerf_desc_t* d, ffn_net_t** out) {
   net->num_layers = nl;
   net->heads.push_back(PackHead{L, 256, 3, 1});        // opacity_out -> out[3]
   net->heads.push_back(PackHead{L + 3, 128, 0, 3});    // color_out   -> out[0..2]
-  if (finalize_net(net) || build_nerf_backward(net, L) || build_ts_program(net)) { ffn_net_destroy(net); return 1; }
+  if (finalize_net(net) || build_nerf_backward(net, L)) { ffn_net_destroy(net); return 1; }
   ConstParams* h = new ConstParams();
   memset(h, 0, sizeof(ConstParams));
   for (int k = 0; k < Fp; ++k) h->freq_pos[k] = d->freq_pos[k];
@@ -550,7 +539,7 @@ extern "C" int ffn_ffmlp_create(int32_t num_hidden, int32_t num_channels, int32_
 extern "C" void ffn_net_destroy(ffn_net_t* net) {
   if (!net) return;
   cudaFree(net->d_wpack); cudaFree(net->d_colmap); cudaFree(net->d_cparams);
-  cudaFree(net->d_ffm_a); cudaFree(net->d_ffm_b); cudaFree(net->d_scratch); cudaFree(net->d_stats); cudaFree(net->d_wpack_bwd); cudaFree(net->d_wpack_ts);
+  cudaFree(net->d_ffm_a); cudaFree(net->d_ffm_b); cudaFree(net->d_scratch); cudaFree(net->d_stats); cudaFree(net->d_wpack_bwd);
   delete net;
 }
 
@@ -585,7 +574,6 @@ extern "C" int ffn_net_pack(ffn_net_t* net, const float* const* weights, const f
   else pack_const_kernel<false><<<1, 256, 0, stream>>>(pa, net->d_cparams, net->d_wpack);
   g_launches += 2;
   CUDA_TRY(cudaGetLastError());
-  if (pack_ts(net, pa, stream)) return 1;
   net->gen = g_gen.fetch_add(1);
   net->packed = true;
   return 0;
@@ -595,20 +583,16 @@ extern "C" int ffn_net_pack(ffn_net_t* net, const float* const* weights, const f
 // launches
 // ============================================================================================
 // one instantiation of the render kernel; the opt-in to 227 KB of dynamic shared memory is set on first use
-template <bool kBF16, int kPass, bool kPair>
-static int launch_instance(const cudaLaunchConfig_t& cfg, const KernelArgs& ka) {
+template <bool kBF16, int kPass>
+static int launch_variant(const cudaLaunchConfig_t& cfg, const KernelArgs& ka) {
   static bool attr_done = false;
   if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(ffn_render_kernel<kBF16, kPass, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(ffn_render_kernel<kBF16, kPass>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kSmemTotal));
     attr_done = true;
   }
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<kBF16, kPass, kPair>, ka));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_render_kernel<kBF16, kPass>, ka));
   return 0;
-}
-template <bool kBF16, int kPass>
-static int launch_variant(const cudaLaunchConfig_t& cfg, const KernelArgs& ka, bool pair) {
-  return pair ? launch_instance<kBF16, kPass, true>(cfg, ka) : launch_instance<kBF16, kPass, false>(cfg, ka);
 }
 
 static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int pass = PASS_INFER) {
@@ -635,13 +619,9 @@ static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int 
   ka.dbg_flags = getenv("FFN_DBG_FLAGS") ? atoi(getenv("FFN_DBG_FLAGS")) : 0;   // bring-up / timing experiments
   static const bool env_stats = getenv("FFN_STATS") != nullptr;
   ka.stats = env_stats ? net->d_stats : nullptr;
-  static const int env_lockstep = getenv("FFN_LOCKSTEP") ? atoi(getenv("FFN_LOCKSTEP")) : 0;
-  ka.lockstep = env_lockstep;
   const long long tiles = (ka.M + kTileM - 1) / kTileM;
   if (tiles > 0x7fffffffLL) return fail("too many rows for one launch");
   ka.num_tiles = (int)tiles;
-  static const bool use_ts = getenv("FFN_USE_TS") != nullptr;   // experimental A-in-TMEM kernel
-  if (pass == PASS_INFER && net->ts_ready && ka.dbg_layer < 0 && use_ts) return launch_ts(net, ka, stream);
   // clusters of 2 CTAs (TMA multicast of the weight stream): even grid, at most one CTA per SM
   int grid = (int)std::min<long long>((tiles + 1) & ~1LL, g_num_sms & ~1);
   cudaLaunchConfig_t cfg;
@@ -651,19 +631,15 @@ static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int 
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  // cta_group::2 ("pair") UMMAs are the default; FFN_PAIR=0 selects the single-CTA variant (read per launch so
-  // that one process can compare both).  A pair UMMA needs N % 16 == 0 in every layer.
-  const char* env_pair = getenv("FFN_PAIR");
-  bool pair = !(env_pair != nullptr && env_pair[0] == '0');
-  for (int l = 0; l < ka.num_layers; ++l) pair = pair && (ka.layers[l].n % 16 == 0);
+  // every UMMA is a cta_group::2 ("pair") instruction: N % 16 == 0 in every layer (N is 256 or 128 here)
+  for (int l = 0; l < ka.num_layers; ++l)
+    if (ka.layers[l].n % 16 != 0) return fail("layer width is not a multiple of 16");
   if (pass == PASS_BWD) {
-    if (launch_variant<true, PASS_BWD>(cfg, ka, pair)) return 1;
+    if (launch_variant<true, PASS_BWD>(cfg, ka)) return 1;
   } else if (pass == PASS_TRAIN_FWD) {
-    if (net->bf16 ? launch_variant<true, PASS_TRAIN_FWD>(cfg, ka, pair)
-                  : launch_variant<false, PASS_TRAIN_FWD>(cfg, ka, pair)) return 1;
+    if (net->bf16 ? launch_variant<true, PASS_TRAIN_FWD>(cfg, ka) : launch_variant<false, PASS_TRAIN_FWD>(cfg, ka)) return 1;
   } else {
-    if (net->bf16 ? launch_variant<true, PASS_INFER>(cfg, ka, pair)
-                  : launch_variant<false, PASS_INFER>(cfg, ka, pair)) return 1;
+    if (net->bf16 ? launch_variant<true, PASS_INFER>(cfg, ka) : launch_variant<false, PASS_INFER>(cfg, ka)) return 1;
   }
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
@@ -801,7 +777,6 @@ extern "C" int ffn_debug_stats(ffn_net_t* net, uint64_t* out32) {
 }
 
 #include "ffn_train.cuh"
-#include "ffn_ts_host.cuh"
 #include "ffn_focus.cuh"
 #include "ffn_raygen.cuh"
 #include "ffn_voxels.cuh"

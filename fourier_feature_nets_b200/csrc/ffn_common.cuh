@@ -18,8 +18,9 @@ constexpr int kActChunks = 4;                  // 256-wide hidden activation
 constexpr int kEncChunk = 4;                   // chunk index of the encoding tile inside a slot
 constexpr int kSlotChunks = 5;
 constexpr int kSlotBytes = kSlotChunks * kChunkBytesA;   // 80 KiB
-constexpr int kWStageBytes = 256 * 128;        // one weight K-chunk (N=256 x K=64): 32 KiB
-constexpr int kWStages = 2;
+// every UMMA spans the CTA pair (cta_group::2): a CTA stages only ITS half of the rows of a weight K-chunk
+constexpr int kWStageBytes = 128 * 128;        // half of a weight K-chunk (N=256 x K=64): 16 KiB per CTA
+constexpr int kWStages = 4;
 constexpr int kSmemW = 0;
 constexpr int kSmemSlot0 = kWStages * kWStageBytes;             // 64 KiB
 constexpr int kSmemMisc = kSmemSlot0 + 2 * kSlotBytes;          // 224 KiB
@@ -29,11 +30,9 @@ constexpr int kSmemTotal = kSmemMisc + kSmemMiscBytes;          // 232448 = 227 
 constexpr int kMaxMmaLayers = 12;
 constexpr int kMaxChunksPerLayer = 6;
 // warps 0-3: weight producer / UMMA issuer / TMEM alloc / ones tile; 4-7, 8-11: epilogue warpgroup of slot 0 / 1.
-// kHelperWG adds warps 12-15 / 16-19 that convert the upper half of the accumulator columns of slot 0 / 1.
-// Measured on B200 (profiles/r01_perf_experiments.md): it does NOT help -- draining the accumulator is bound by
-// the ~64 B/clk TMEM read port, not by per-warp latency -- so it is compiled out.
-constexpr bool kHelperWG = false;
-constexpr int kThreads = kHelperWG ? 640 : 384;
+// (A helper warpgroup per slot, lock-step weight sharing between the slots, single-CTA UMMAs and an A-operand-in-TMEM
+// variant were measured in round 1 and removed: profiles/r01_perf_experiments.md.)
+constexpr int kThreads = 384;
 
 // epilogue kinds
 enum : uint8_t {
@@ -142,7 +141,6 @@ struct KernelArgs {
   int32_t bwd_first_save;      //           dz_out slot it is written to
   int32_t bwd_sigma_chunk;     //           1: d(sigma_raw) goes to column 0 of the encoding chunk
   int32_t num_tiles;
-  int32_t lockstep;            // 1: both slots run the same layer and share each weight stage (see kernel)
   int32_t dz_tma;              // PASS_BWD: 1 = dz_out is written by TMA stores of the bf16 A tile (dz_map)
   int32_t sh_tma;              // PASS_TRAIN_FWD: 1 = save_h is written by TMA stores of the A tile (sh_map)
   alignas(64) CUtensorMap dz_map;   // [n_dz][M][256] bf16, boxes of 64 columns x 32 rows, SWIZZLE_128B

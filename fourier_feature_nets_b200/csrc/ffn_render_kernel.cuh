@@ -1,10 +1,11 @@
 // The fused render kernel: sampling -> Fourier encoding -> MLP on tcgen05 -> compositing.
 //
-// One persistent CTA per SM, 384 threads:
-//   warp 0      weight producer: streams the packed (pre-swizzled) weight K-chunks of every
-//               layer through a 2-stage shared-memory ring with the bulk-copy (TMA) engine
-//   warp 1      UMMA issuer: one lane issues tcgen05.mma (M=128, N=256|128, K=16) for the
-//               tile in slot 0 then slot 1 of each layer, committing to mbarriers
+// One persistent CTA per SM, clusters of two CTAs (one TPC), 384 threads per CTA:
+//   warp 0      weight producer: streams MY half of the rows of the packed (pre-swizzled) weight K-chunks of
+//               every layer through a 4-stage shared-memory ring with the bulk-copy (TMA) engine
+//   warp 1      rank 0: UMMA issuer, one elected lane issues tcgen05.mma.cta_group::2 (M=256: 128 rows per CTA,
+//               N=256|128, K=16) for the tile in slot 0 then slot 1 of each layer, committing to mbarriers of both
+//               CTAs; rank 1: relays "my half of the weight stage has landed" to rank 0
 //   warp 2      allocates / frees the 512 TMEM columns (two 128x256 fp32 accumulators)
 //   warps 4-7   epilogue warpgroup of slot 0     } thread == row == sample: inputs, encoding,
 //   warps 8-11  epilogue warpgroup of slot 1     } TMEM -> bias/ReLU -> fp16 A tile, heads,
@@ -303,18 +304,19 @@ __device__ __forceinline__ void head_layer_epilogue(uint32_t taddr_base, int nbl
 // ----------------------------------------------------------------------------------------
 // the kernel
 // ----------------------------------------------------------------------------------------
-// kPair: the two CTAs of the cluster execute every UMMA together (tcgen05 cta_group::2, M = 256): each CTA
+// The two CTAs of the cluster execute every UMMA together (tcgen05 cta_group::2, M = 256): each CTA
 // supplies its own 128 rows of A and HALF of B's rows, so B operand reads, weight fills and the bytes the ring
 // must keep in flight all halve per SM.  Only rank 0's warp 1 issues; rank 1's warp 1 relays "my half of the
-// weight stage has landed" to rank 0.  Epilogues are unchanged (each CTA drains its own TMEM lanes).
+// weight stage has landed" to rank 0.  Each CTA drains its own TMEM lanes.
 // (Accumulating a 256-wide layer as two N = 128 halves so that half of the drain overlaps the second half's
 // UMMAs was tried and dropped: an SS-mode UMMA costs ~128 cycles whatever N is -- the 4 KB A operand read --
 // so the halves double the tensor time; profiles/r01_perf_experiments.md.)
-template <bool kBF16, int kPass, bool kPair = false>
+template <bool kBF16, int kPass>
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_render_kernel(const __grid_constant__ KernelArgs args) {
-  constexpr int kStages = kPair ? 4 : kWStages;
-  constexpr uint32_t kStageBytes = kPair ? kWStageBytes / 2 : kWStageBytes;
+  constexpr bool kPair = true;
+  constexpr int kStages = kWStages;
+  constexpr uint32_t kStageBytes = kWStageBytes;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = ptx::smem_u32(smem);
   const int warp = threadIdx.x >> 5;
@@ -337,13 +339,12 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
-      // kPair: rank 0's "full" barrier also collects rank 1's relay arrive; "empty" comes from one multicast commit.
-      // !kPair: "empty" is released by the UMMA issuers of BOTH CTAs (multicast weight stream)
-      ptx::mbar_init(bar_w_full + 8 * i, (kPair && cta_rank == 0) ? 2 : 1);
-      ptx::mbar_init(bar_w_empty + 8 * i, kPair ? 1 : 2);
+      // rank 0's "full" barrier also collects rank 1's relay arrive; "empty" comes from one multicast commit
+      ptx::mbar_init(bar_w_full + 8 * i, cta_rank == 0 ? 2 : 1);
+      ptx::mbar_init(bar_w_empty + 8 * i, 1);
     }
     for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(bar_a_ready + 8 * i, (kHelperWG ? 8 : 4) * (kPair ? 2 : 1));   // one arrive per epilogue warp
+      ptx::mbar_init(bar_a_ready + 8 * i, 8);   // one arrive per epilogue warp of BOTH CTAs
       ptx::mbar_init(bar_acc_full + 16 * i, 1);
     }
     ptx::fence_mbar_init();
@@ -356,13 +357,8 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
     ptx::fence_proxy_async();
   }
   if (warp == 2) {
-    if constexpr (kPair) {
-      ptx::tmem_alloc_pair(ptx::smem_u32(tmem_ptr_smem), 512);
-      ptx::tmem_relinquish_pair();
-    } else {
-      ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), 512);
-      ptx::tmem_relinquish();
-    }
+    ptx::tmem_alloc_pair(ptx::smem_u32(tmem_ptr_smem), 512);
+    ptx::tmem_relinquish_pair();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -391,8 +387,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       for (int l = 0; l < L; ++l) {
         const LayerDesc& ld = args.layers[l];
         const uint32_t bytes = (uint32_t)ld.n * 128u;
-        const int npass = (!kPair && args.lockstep) ? 1 : nslots;    // lock-step: one weight stream feeds both slots
-        for (int s = 0; s < npass; ++s) {
+        for (int s = 0; s < nslots; ++s) {
           // chunk -1 = the layer's bias tile (N x 32 B), then the weight K-chunks
           for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
             ptx::mbar_wait(bar_w_empty + 8 * stage, phase ^ 1u);
@@ -401,17 +396,10 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
               const uint8_t* src = c < 0 ? args.wpack + ld.bias_off
                                          : args.wpack + ld.w_offset + (size_t)c * bytes;
               const uint32_t hb = nbytes >> 1;      // my half
-              if constexpr (kPair) {
-                // my half of B's rows stays in MY shared memory; cta_group::2 reads the other half from the peer.
-                // Rows are contiguous in both the SW128 and the bias-tile layout.
-                ptx::mbar_arrive_expect_tx(bar_w_full + 8 * stage, hb);
-                ptx::bulk_g2s(smem_base + kSmemW + stage * kStageBytes, src + cta_rank * hb, hb, bar_w_full + 8 * stage);
-              } else {
-                // multicast my half to both CTAs
-                ptx::mbar_arrive_expect_tx(bar_w_full + 8 * stage, nbytes);
-                ptx::bulk_g2s_mc(smem_base + kSmemW + stage * kStageBytes + cta_rank * hb, src + cta_rank * hb, hb,
-                                 bar_w_full + 8 * stage, (uint16_t)3);
-              }
+              // my half of B's rows stays in MY shared memory; cta_group::2 reads the other half from the peer.
+              // Rows are contiguous in both the SW128 and the bias-tile layout.
+              ptx::mbar_arrive_expect_tx(bar_w_full + 8 * stage, hb);
+              ptx::bulk_g2s(smem_base + kSmemW + stage * kStageBytes, src + cta_rank * hb, hb, bar_w_full + 8 * stage);
             }
             __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -419,7 +407,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
         }
       }
     }
-  } else if (warp == 1 && kPair && cta_rank != 0) {
+  } else if (warp == 1 && cta_rank != 0) {
     // ================================================================ rank 1: weight-stage relay
     uint32_t stage = 0, phase = 0;
     for (int kp = 0; kp < my_tiles; kp += 2) {
@@ -445,43 +433,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       const int nslots = min(2, my_tiles - kp);
       for (int l = 0; l < L; ++l) {
         const LayerDesc& ld = args.layers[l];
-        const uint32_t idesc = kPair ? ptx::make_idesc_f16_m256(ld.n, kBF16) : ptx::make_idesc_f16(ld.n, kBF16);
-        if (!kPair && args.lockstep) {
-          // ---- lock-step schedule: both slots run layer l together and share every weight stage
-          long long t0 = prof ? clock64() : 0;
-          for (int s = 0; s < nslots; ++s) {
-            ptx::mbar_wait(bar_a_ready + 8 * s, a_phase[s]);
-            a_phase[s] ^= 1u;
-          }
-          if (prof) t_wait_a += clock64() - t0;
-          ptx::tc_fence_after();
-          uint32_t accumulate = ld.accumulate;
-          for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
-            t0 = prof ? clock64() : 0;
-            ptx::mbar_wait(bar_w_full + 8 * stage, phase);
-            if (prof) t_wait_w += clock64() - t0;
-            ptx::tc_fence_after();
-            const uint32_t b_addr = smem_base + kSmemW + stage * kWStageBytes;
-            const bool last_chunk = c == ld.n_chunks - 1;
-            for (int s = 0; s < nslots; ++s) {
-              const uint32_t d_tmem = tmem_base + (uint32_t)s * 256u;
-              const uint32_t slot_base = smem_base + kSmemSlot0 + s * kSlotBytes;
-              if (c < 0)
-                ptx::umma_chunk_ss(d_tmem, ptx::make_kmajor_nosw_desc(smem_base + kSmemOnes, 128u, 0u),
-                                   ptx::make_kmajor_nosw_desc(b_addr, kBiasTileLBO, kBiasTileSBO), idesc, accumulate, 1);
-              else
-                ptx::umma_chunk_ss(d_tmem, ptx::make_kmajor_sw128_desc(slot_base + (uint32_t)ld.src[c] * kChunkBytesA),
-                                   ptx::make_kmajor_sw128_desc(b_addr), idesc, accumulate, ld.ksteps[c]);
-              // slot 0's accumulator is complete one chunk-time before slot 1's: release its epilogue first
-              if (s < nslots - 1 && last_chunk) ptx::umma_commit_warp(bar_acc_full + 16 * s, 0u, 0u);
-            }
-            accumulate = 1u;
-            ptx::umma_commit_warp_mc(bar_w_empty + 8 * stage, last_chunk ? bar_acc_full + 16 * (nslots - 1) : 0u);
-            __syncwarp();
-            if (++stage == kWStages) { stage = 0; phase ^= 1u; }
-          }
-          continue;
-        }
+        const uint32_t idesc = ptx::make_idesc_f16_m256(ld.n, kBF16);
         for (int s = 0; s < nslots; ++s) {
           long long t0 = prof ? clock64() : 0;
           ptx::mbar_wait(bar_a_ready + 8 * s, a_phase[s]);   // kPair: arrivals from the epilogue warps of both CTAs
@@ -508,13 +460,8 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
                                             : ptx::make_kmajor_sw128_desc(b_addr);
               const int ks_n = c < 0 ? 1 : ld.ksteps[c];
               const uint32_t full_bar = c == ld.n_chunks - 1 ? bar_acc_full + 16 * s : 0u;
-              if constexpr (kPair) {
-                ptx::umma_chunk_ss_pair(d_tmem, a_desc, b_desc, idesc, accumulate, ks_n);
-                ptx::umma_commit_warp_pair(bar_w_empty + 8 * stage, full_bar);
-              } else {
-                ptx::umma_chunk_ss(d_tmem, a_desc, b_desc, idesc, accumulate, ks_n);
-                ptx::umma_commit_warp_mc(bar_w_empty + 8 * stage, full_bar);
-              }
+              ptx::umma_chunk_ss_pair(d_tmem, a_desc, b_desc, idesc, accumulate, ks_n);
+              ptx::umma_commit_warp_pair(bar_w_empty + 8 * stage, full_bar);
               accumulate = 1u;
             }
             __syncwarp();
@@ -532,7 +479,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
   } else if (warp >= 4) {
     // ================================================================ epilogue warpgroups
     const int slot = ((warp - 4) >> 2) & 1;
-    const int grp = warp >= 12 ? 1 : 0;            // 0: primary warpgroup of the slot, 1: helper (upper columns only)
+    constexpr int grp = 0;                         // (one warpgroup per slot)
     const int wq = warp & 3;                       // TMEM lane quadrant of this warp
     const int row = wq * 32 + lane;                // row inside the tile == TMEM lane
     const uint32_t row7 = (uint32_t)row & 7u;
@@ -547,7 +494,6 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
     uint32_t acc_phase = 0;
     const int S = args.S;
     const bool eprof = args.stats != nullptr && warp == 4 && lane == 0;
-    float* sc_sig = sc_part + 32;                  // [128] helper's partial sigma head
     long long e_wait = 0, e_work = 0, e_front = 0, e_back = 0, e_t = 0;
 
     // outputs of one finished tile: raw rows and / or the fused compositing (ray_caster.py:67-93 + utils.py:72-97).
@@ -791,7 +737,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       for (int l = 0; l < L; ++l) {
         const LayerDesc& ld = args.layers[l];
         const int nblk_all = ld.n >> 5;                 // 32-column blocks of this layer (8 or 4)
-        const int nblk_grp = kHelperWG ? nblk_all >> 1 : nblk_all;   // ... converted by this warpgroup
+        const int nblk_grp = nblk_all;
         const bool general = ld.epi == EPI_RELU_HEAD || ld.sigma_head || args.dbg_layer == l;
         ptx::mbar_wait(my_acc_full, acc_phase);
         acc_phase ^= 1u;
@@ -838,7 +784,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
 #pragma unroll
           for (int o = 0; o < 4; ++o)
             if (o < ld.head_n) out[o] = hacc[o] + c_params.head_b[o];
-        } else if (!kHelperWG && ld.sigma_head && ld.epi == EPI_RELU_ACT && args.dbg_layer != l && ld.n == 256) {
+        } else if (ld.sigma_head && ld.epi == EPI_RELU_ACT && args.dbg_layer != l && ld.n == 256) {
           // trunk layer that also feeds opacity_out: the lean path plus one fp32 dot product
           const size_t rg = valid ? (size_t)row_g : 0;
           __nv_bfloat16* gh = nullptr;
@@ -980,13 +926,8 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           pend = false;
         }
         if (ld.sigma_head) {
-          // sigma_raw = w_op . h + b: add the helper's partial dot product (after the UMMA issuer was released)
-          if constexpr (kHelperWG) {
-            if (grp != 0) sc_sig[row] = out[3];
-            ptx::named_bar_sync(3 + slot, 256);
-            if (grp == 0) out[3] += sc_sig[row];
-          }
-          if (grp == 0) out[3] += c_params.head_b[3];
+          // sigma_raw = w_op . h + b
+          out[3] += c_params.head_b[3];
         }
         if (eprof) {
           const long long n = clock64();
@@ -1027,8 +968,7 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
   __syncthreads();
   ptx::cluster_sync_all();     // the peer may still multicast into / commit onto this CTA's shared memory
   if (warp == 2) {
-    if constexpr (kPair) ptx::tmem_dealloc_pair(tmem_base, 512);
-    else ptx::tmem_dealloc(tmem_base, 512);
+    ptx::tmem_dealloc_pair(tmem_base, 512);
   }
 }
 

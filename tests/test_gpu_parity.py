@@ -323,34 +323,6 @@ def test_full_size_properties(golden_nerf):
     assert eng.net.nan_flag() == 0
 
 
-@pytest.mark.parametrize("env", [{"FFN_USE_TS": "1"}, {"FFN_PAIR": "0", "FFN_LOCKSTEP": "1"}, {"FFN_PAIR": "0"}])
-def test_alternative_kernel_schedules_stay_parity_green(env):
-    """The evaluated-but-not-default variants (A operand in TMEM; single-CTA UMMAs with and without lock-step
-    weight sharing) are selected by environment variables read at the first launch: run them in a fresh process."""
-    import subprocess
-    import sys
-    from conftest import ROOT
-    code = r"""
-import os, sys, numpy as np, torch
-sys.path.insert(0, %r)
-import fourier_feature_nets_b200 as ffn
-g = np.load(os.path.join(%r, "nerf_render.npz"))
-m = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True)
-m.load_state_dict({k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w.")})
-m = m.cuda().eval()
-s = ffn.RaySamples(*[torch.from_numpy(g[k]).cuda() for k in ("positions", "view_directions", "t_values")], None)
-with torch.no_grad():
-    out = ffn.Raycaster(m).render(s, True)
-err = float(np.abs(out.color.cpu().numpy() - g["color"]).max())
-mis = float((out.depth.cpu().numpy() != g["depth"]).mean())
-print("ERR", err, mis)
-assert err <= 2.5e-3 and mis <= 0.02
-""" % (ROOT, GOLDEN)
-    res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True,
-                         timeout=300)
-    assert res.returncode == 0 and "ERR" in res.stdout, res.stdout[-1000:] + res.stderr[-2000:]
-
-
 def test_engine_follows_changed_encoding_buffers():
     """a GaussianFourierMLP that has already rendered on CUDA and then receives ``load_state_dict``
     of a checkpoint with ANOTHER B matrix must render with the new B (the encoding buffers are baked into the C
