@@ -16,7 +16,8 @@ from typing import List, Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libffn_b200.so")
+# FFN_LIB: load another build of the same ABI (A/B timing of two kernel versions inside one GPU session)
+LIB_PATH = os.environ.get("FFN_LIB") or os.path.join(_HERE, "libffn_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 FFN_MAX_LAYERS = 16

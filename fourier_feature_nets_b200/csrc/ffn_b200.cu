@@ -13,6 +13,7 @@
 #include "ffn_tma_host.cuh"
 #include "ffn_common.cuh"
 #include "ffn_render_kernel.cuh"
+#include "ffn_infer_kernel.cuh"
 
 using namespace ffn;
 
@@ -81,6 +82,8 @@ struct ffn_net {
   unsigned long long* d_stats = nullptr;   // issuer-warp cycle counters (FFN_STATS=1)
   float* d_scratch = nullptr;   // grow-only temp (raw outputs for the non-fused path)
   size_t scratch_bytes = 0;
+  uint8_t* d_ray_scratch = nullptr;   // grow-only: per-ray compositing partials + counters (rays that straddle tiles)
+  size_t ray_scratch_bytes = 0;
   long long gen = 0;            // bumped by every pack
   bool packed = false;
   // training (NeRF handles): backward program + slot bookkeeping
@@ -338,10 +341,6 @@ static int finalize_net(ffn_net* net) {
       return fail("libffn_b200 needs an sm_100 (B200) device, found sm_" + std::to_string(prop.major) +
                   std::to_string(prop.minor));
     g_num_sms = prop.multiProcessorCount;
-    CUDA_TRY(cudaFuncSetAttribute(ffn_render_kernel<false, PASS_INFER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kSmemTotal));
-    CUDA_TRY(cudaFuncSetAttribute(ffn_render_kernel<true, PASS_INFER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kSmemTotal));
   }
   return 0;
 }
@@ -539,7 +538,7 @@ extern "C" int ffn_ffmlp_create(int32_t num_hidden, int32_t num_channels, int32_
 extern "C" void ffn_net_destroy(ffn_net_t* net) {
   if (!net) return;
   cudaFree(net->d_wpack); cudaFree(net->d_colmap); cudaFree(net->d_cparams);
-  cudaFree(net->d_ffm_a); cudaFree(net->d_ffm_b); cudaFree(net->d_scratch); cudaFree(net->d_stats); cudaFree(net->d_wpack_bwd);
+  cudaFree(net->d_ffm_a); cudaFree(net->d_ffm_b); cudaFree(net->d_scratch); cudaFree(net->d_ray_scratch); cudaFree(net->d_stats); cudaFree(net->d_wpack_bwd);
   delete net;
 }
 
@@ -583,6 +582,16 @@ extern "C" int ffn_net_pack(ffn_net_t* net, const float* const* weights, const f
 // launches
 // ============================================================================================
 // one instantiation of the render kernel; the opt-in to 227 KB of dynamic shared memory is set on first use
+template <bool kBF16>
+static int launch_infer(const cudaLaunchConfig_t& cfg, const KernelArgs& ka) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(ffn_infer_kernel<kBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    attr_done = true;
+  }
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_infer_kernel<kBF16>, ka));
+  return 0;
+}
 template <bool kBF16, int kPass>
 static int launch_variant(const cudaLaunchConfig_t& cfg, const KernelArgs& ka) {
   static bool attr_done = false;
@@ -639,7 +648,7 @@ static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int 
   } else if (pass == PASS_TRAIN_FWD) {
     if (net->bf16 ? launch_variant<true, PASS_TRAIN_FWD>(cfg, ka) : launch_variant<false, PASS_TRAIN_FWD>(cfg, ka)) return 1;
   } else {
-    if (net->bf16 ? launch_variant<true, PASS_INFER>(cfg, ka) : launch_variant<false, PASS_INFER>(cfg, ka)) return 1;
+    if (net->bf16 ? launch_infer<true>(cfg, ka) : launch_infer<false>(cfg, ka)) return 1;
   }
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
@@ -655,7 +664,31 @@ static int ensure_scratch(ffn_net* net, size_t bytes) {
   return 0;
 }
 
+// training forward: the in-kernel compositing of ffn_render_kernel needs rays aligned with the 128-row tiles
 static bool fusable(int S) { return S >= 1 && S <= 128 && (S & (S - 1)) == 0; }
+
+// inference: the compositing of ffn_infer_kernel handles any S; rays that straddle 128-row tiles (128 % S != 0) leave
+// per-tile partials in a scratch buffer owned by the net handle and are finished by the last CTA to arrive
+static int setup_fused_infer(ffn_net* net, KernelArgs& ka, long long R, int S, float* color, float* alpha, float* depth,
+                             cudaStream_t stream) {
+  ka.fused = 1; ka.rgb = color; ka.alpha = alpha; ka.depth = depth;
+  ka.ray_part = nullptr; ka.ray_cnt = nullptr; ka.nseg_max = 1;
+  if (kTileM % S == 0) return 0;
+  const int nseg_max = (S + kTileM - 2) / kTileM + 1;
+  const size_t part_bytes = ((size_t)R * nseg_max * 32 + 255) & ~(size_t)255;
+  const size_t need = part_bytes + (size_t)R * 4;
+  if (net->ray_scratch_bytes < need) {
+    if (net->d_ray_scratch) CUDA_TRY(cudaFree(net->d_ray_scratch));   // synchronises: safe w.r.t. in-flight users
+    net->d_ray_scratch = nullptr; net->ray_scratch_bytes = 0;
+    CUDA_TRY(cudaMalloc(&net->d_ray_scratch, need));
+    net->ray_scratch_bytes = need;
+  }
+  ka.ray_part = reinterpret_cast<float*>(net->d_ray_scratch);
+  ka.ray_cnt = reinterpret_cast<int32_t*>(net->d_ray_scratch + part_bytes);
+  ka.nseg_max = nseg_max;
+  CUDA_TRY(cudaMemsetAsync(ka.ray_cnt, 0, (size_t)R * 4, stream));
+  return 0;
+}
 
 static int launch_composite(const float* raw, const float* t, long long R, int S, float* rgb,
                             float* alpha, float* depth, float* weights, int* nan_flag,
@@ -705,14 +738,8 @@ extern "C" int ffn_render_samples(ffn_net_t* net, const float* positions, const 
   memset(&ka, 0, sizeof(ka));
   ka.mode = MODE_SAMPLES; ka.pos = positions; ka.dir = view_directions; ka.tvals = t_values;
   ka.M = (long long)R * S; ka.S = S; ka.dbg_layer = -1; ka.nan_flag = nan_flag;
-  if (fusable(S)) {
-    ka.fused = 1; ka.rgb = color; ka.alpha = alpha; ka.depth = depth;
-    return launch_render(net, ka, stream);
-  }
-  if (ensure_scratch(net, (size_t)ka.M * 16)) return 1;
-  ka.fused = 0; ka.raw = net->d_scratch;
-  if (launch_render(net, ka, stream)) return 1;
-  return launch_composite(net->d_scratch, t_values, R, S, color, alpha, depth, nullptr, nan_flag, stream);
+  if (setup_fused_infer(net, ka, R, S, color, alpha, depth, stream)) return 1;
+  return launch_render(net, ka, stream);
 }
 
 extern "C" int ffn_render_rays(ffn_net_t* net, const float* starts, const float* directions,
@@ -730,19 +757,8 @@ extern "C" int ffn_render_rays(ffn_net_t* net, const float* starts, const float*
   ka.mode = MODE_RAYS; ka.org = starts; ka.dir = directions; ka.near_ = near_; ka.far_ = far_;
   ka.lin = lin; ka.jitter = jitter; ka.stratified = stratified; ka.seed = seed; ka.ray_offset = ray_offset;
   ka.M = (long long)R * S; ka.S = S; ka.dbg_layer = -1; ka.nan_flag = nan_flag; ka.t_out = t_out;
-  if (fusable(S)) {
-    ka.fused = 1; ka.rgb = color; ka.alpha = alpha; ka.depth = depth;
-    return launch_render(net, ka, stream);
-  }
-  // general S: raw outputs + t values to scratch, then the stand-alone compositor
-  const size_t raw_bytes = (size_t)ka.M * 16;
-  const size_t need = raw_bytes + (t_out ? 0 : (size_t)ka.M * 4);
-  if (ensure_scratch(net, need)) return 1;
-  ka.fused = 0; ka.raw = net->d_scratch;
-  float* tbuf = t_out ? t_out : reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(net->d_scratch) + raw_bytes);
-  ka.t_out = tbuf;
-  if (launch_render(net, ka, stream)) return 1;
-  return launch_composite(net->d_scratch, tbuf, R, S, color, alpha, depth, nullptr, nan_flag, stream);
+  if (setup_fused_infer(net, ka, R, S, color, alpha, depth, stream)) return 1;
+  return launch_render(net, ka, stream);
 }
 
 extern "C" int ffn_composite(const float* raw, const float* t_values, int64_t R, int32_t S, float* color,

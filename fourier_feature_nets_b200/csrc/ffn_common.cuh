@@ -116,7 +116,10 @@ struct KernelArgs {
   int32_t stratified;
   long long M;                 // total rows
   int32_t S;                   // samples per ray (fused / rays modes)
-  int32_t fused;               // 1: composite in-kernel (S power of two <= 128)
+  int32_t fused;               // 1: composite in-kernel (inference: any S; training forward: S power of two <= 128)
+  float* ray_part;             // inference, rays that straddle 128-row tiles (128 % S != 0): [R][nseg_max][8] partials
+  int32_t* ray_cnt;            //   ... and [R] arrival counters (zeroed before the launch)
+  int32_t nseg_max;            //   tiles a ray can touch: (S + 126) / 128 + 1
   // outputs
   float* raw;                  // (M,4) when !fused
   float* t_out;                // (M) optional (RAYS)

@@ -145,14 +145,8 @@ extern "C" int ffn_render_rays_t(ffn_net_t* net, const float* starts, const floa
   memset(&ka, 0, sizeof(ka));
   ka.mode = MODE_RAYS_T; ka.org = starts; ka.dir = directions; ka.tvals = t_values;
   ka.M = (long long)R * S; ka.S = S; ka.dbg_layer = -1; ka.nan_flag = nan_flag;
-  if (fusable(S)) {
-    ka.fused = 1; ka.rgb = color; ka.alpha = alpha; ka.depth = depth;
-    return launch_render(net, ka, stream);
-  }
-  if (ensure_scratch(net, (size_t)ka.M * 16)) return 1;
-  ka.fused = 0; ka.raw = net->d_scratch;
-  if (launch_render(net, ka, stream)) return 1;
-  return launch_composite(net->d_scratch, t_values, R, S, color, alpha, depth, nullptr, nan_flag, stream);
+  if (setup_fused_infer(net, ka, R, S, color, alpha, depth, stream)) return 1;
+  return launch_render(net, ka, stream);
 }
 
 // coarse pass + focus sampling in one call: sigma of `coarse` at the un-jittered S_c samples (scratch inside

@@ -15,6 +15,7 @@
 #pragma once
 #include "ffn_common.cuh"
 #include "ffn_ptx.cuh"
+#include "ffn_pipeline.cuh"
 
 namespace ffn {
 
@@ -204,8 +205,8 @@ __device__ __forceinline__ void apply_sign_mask(uint32_t (&v)[32], uint32_t w) {
 //   kPass = PASS_TRAIN_FWD  + bf16 copy to gh, sign words to gm (when kRelu)
 //   kPass = PASS_BWD        kMask: multiply by ReLU' from the sign words at gm; A tile and HBM copy in bf16
 //   kSigma: additionally the fp32 dot product of the activated row with head 3 (opacity_out, nerf_model.py:117)
-//           into *hsum, columns in ascending order; needs b0 == 0 as a literal so that the weights become
-//           constant-bank operands of the FFMAs
+//           as four partial sums hsum[0..3] (the caller adds them); needs b0 == 0 as a literal so that the weights
+//           become constant-bank operands of the FFMAs
 template <bool kBF16, bool kRelu, int kPass, bool kMask, bool kSigma = false>
 __device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int b0, int nblk, uint32_t act_row,
                                                     uint32_t row7, __nv_bfloat16* gh, uint32_t* gm,
@@ -222,11 +223,17 @@ __device__ __forceinline__ void lean_layer_epilogue(uint32_t taddr_base, int b0,
     const uint32_t chunk_row = act_row + (uint32_t)(b >> 1) * kChunkBytesA;
     const uint32_t u0 = (uint32_t)(b & 1) * 4u;
     if constexpr (kSigma) {
-      float a = *hsum;
+      // four independent partial sums (hsum[0..3], column j -> sum j & 3): one dependent chain of 256 FFMAs costs
+      // 256 x 4 cycles of latency per layer, four chains issue back to back
+      float a0 = hsum[0], a1 = hsum[1], a2 = hsum[2], a3 = hsum[3];
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        a = fmaf(kRelu ? fmaxf(__uint_as_float(v[j]), 0.f) : __uint_as_float(v[j]), c_params.head_w[3][b * 32 + j], a);
-      *hsum = a;
+      for (int j = 0; j < 32; j += 4) {
+        a0 = fmaf(kRelu ? fmaxf(__uint_as_float(v[j + 0]), 0.f) : __uint_as_float(v[j + 0]), c_params.head_w[3][b * 32 + j + 0], a0);
+        a1 = fmaf(kRelu ? fmaxf(__uint_as_float(v[j + 1]), 0.f) : __uint_as_float(v[j + 1]), c_params.head_w[3][b * 32 + j + 1], a1);
+        a2 = fmaf(kRelu ? fmaxf(__uint_as_float(v[j + 2]), 0.f) : __uint_as_float(v[j + 2]), c_params.head_w[3][b * 32 + j + 2], a2);
+        a3 = fmaf(kRelu ? fmaxf(__uint_as_float(v[j + 3]), 0.f) : __uint_as_float(v[j + 3]), c_params.head_w[3][b * 32 + j + 3], a3);
+      }
+      hsum[0] = a0; hsum[1] = a1; hsum[2] = a2; hsum[3] = a3;
     }
     if constexpr (kPass == PASS_BWD) {
       if constexpr (kMask) apply_sign_mask(v, mwords[b]);
@@ -316,7 +323,6 @@ __global__ void __launch_bounds__(kThreads, 1)
 ffn_render_kernel(const __grid_constant__ KernelArgs args) {
   constexpr bool kPair = true;
   constexpr int kStages = kWStages;
-  constexpr uint32_t kStageBytes = kWStageBytes;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = ptx::smem_u32(smem);
   const int warp = threadIdx.x >> 5;
@@ -379,103 +385,15 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
   const int my_tiles = (sched_tiles + sched_units - 1) / sched_units;
   const int L = args.num_layers;
 
+  PipeCtx pc;
+  pc.smem_base = smem_base; pc.bar_w_full = bar_w_full; pc.bar_w_empty = bar_w_empty; pc.bar_a_ready = bar_a_ready;
+  pc.bar_acc_full = bar_acc_full; pc.cta_rank = cta_rank; pc.tmem_base = tmem_base; pc.my_tiles = my_tiles; pc.L = L;
   if (warp == 0) {
-    // ================================================================ weight producer
-    uint32_t stage = 0, phase = 0;
-    for (int kp = 0; kp < my_tiles; kp += 2) {
-      const int nslots = min(2, my_tiles - kp);
-      for (int l = 0; l < L; ++l) {
-        const LayerDesc& ld = args.layers[l];
-        const uint32_t bytes = (uint32_t)ld.n * 128u;
-        for (int s = 0; s < nslots; ++s) {
-          // chunk -1 = the layer's bias tile (N x 32 B), then the weight K-chunks
-          for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
-            ptx::mbar_wait(bar_w_empty + 8 * stage, phase ^ 1u);
-            if (lane == 0) {
-              const uint32_t nbytes = c < 0 ? (uint32_t)ld.n * 32u : bytes;
-              const uint8_t* src = c < 0 ? args.wpack + ld.bias_off
-                                         : args.wpack + ld.w_offset + (size_t)c * bytes;
-              const uint32_t hb = nbytes >> 1;      // my half
-              // my half of B's rows stays in MY shared memory; cta_group::2 reads the other half from the peer.
-              // Rows are contiguous in both the SW128 and the bias-tile layout.
-              ptx::mbar_arrive_expect_tx(bar_w_full + 8 * stage, hb);
-              ptx::bulk_g2s(smem_base + kSmemW + stage * kStageBytes, src + cta_rank * hb, hb, bar_w_full + 8 * stage);
-            }
-            __syncwarp();
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
-          }
-        }
-      }
-    }
+    weight_producer(args, pc, lane);
   } else if (warp == 1 && cta_rank != 0) {
-    // ================================================================ rank 1: weight-stage relay
-    uint32_t stage = 0, phase = 0;
-    for (int kp = 0; kp < my_tiles; kp += 2) {
-      const int nslots = min(2, my_tiles - kp);
-      for (int l = 0; l < L; ++l) {
-        const LayerDesc& ld = args.layers[l];
-        const int nst = nslots * (ld.n_chunks + (ld.has_bias ? 1 : 0));
-        for (int i = 0; i < nst; ++i) {
-          ptx::mbar_wait(bar_w_full + 8 * stage, phase);        // my half has landed in my shared memory
-          if (lane == 0) ptx::mbar_arrive_remote_relaxed(bar_w_full + 8 * stage, 0u);
-          __syncwarp();
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
+    weight_relay(args, pc, lane);
   } else if (warp == 1) {
-    // ================================================================ UMMA issuer
-    uint32_t stage = 0, phase = 0;
-    uint32_t a_phase[2] = {0u, 0u};
-    const bool prof = args.stats != nullptr;
-    long long t_wait_a = 0, t_wait_w = 0, t_begin = prof ? clock64() : 0;
-    for (int kp = 0; kp < my_tiles; kp += 2) {
-      const int nslots = min(2, my_tiles - kp);
-      for (int l = 0; l < L; ++l) {
-        const LayerDesc& ld = args.layers[l];
-        const uint32_t idesc = ptx::make_idesc_f16_m256(ld.n, kBF16);
-        for (int s = 0; s < nslots; ++s) {
-          long long t0 = prof ? clock64() : 0;
-          ptx::mbar_wait(bar_a_ready + 8 * s, a_phase[s]);   // kPair: arrivals from the epilogue warps of both CTAs
-          if (prof) t_wait_a += clock64() - t0;
-          a_phase[s] ^= 1u;
-          ptx::tc_fence_after();
-          const uint32_t slot_base = smem_base + kSmemSlot0 + s * kSlotBytes;
-          const uint32_t d_tmem = tmem_base + (uint32_t)s * 256u;
-          uint32_t accumulate = ld.accumulate;
-          for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
-            t0 = prof ? clock64() : 0;
-            // kPair: completes on my half's bytes + the peer's relay arrive; the operands themselves are read
-            // through the async proxy, so a CTA-scope wait is enough (a cluster-scope acquire costs ~a fence each)
-            ptx::mbar_wait(bar_w_full + 8 * stage, phase);
-            if (prof) t_wait_w += clock64() - t0;
-            ptx::tc_fence_after();
-            {
-              // whole (converged) warp, one elected lane issues: see ptx::umma_chunk_ss
-              const uint32_t b_addr = smem_base + kSmemW + stage * kStageBytes;
-              const uint64_t a_desc = c < 0 ? ptx::make_kmajor_nosw_desc(smem_base + kSmemOnes, 128u, 0u)
-                                            : ptx::make_kmajor_sw128_desc(slot_base + (uint32_t)ld.src[c] * kChunkBytesA);
-              // c < 0: D = ones(128x16) . bias_tile(Nx16)^T : every row of the accumulator starts at the bias
-              const uint64_t b_desc = c < 0 ? ptx::make_kmajor_nosw_desc(b_addr, kBiasTileLBO, kBiasTileSBO)
-                                            : ptx::make_kmajor_sw128_desc(b_addr);
-              const int ks_n = c < 0 ? 1 : ld.ksteps[c];
-              const uint32_t full_bar = c == ld.n_chunks - 1 ? bar_acc_full + 16 * s : 0u;
-              ptx::umma_chunk_ss_pair(d_tmem, a_desc, b_desc, idesc, accumulate, ks_n);
-              ptx::umma_commit_warp_pair(bar_w_empty + 8 * stage, full_bar);
-              accumulate = 1u;
-            }
-            __syncwarp();
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
-          }
-        }
-      }
-    }
-    if (prof && lane == 0) {
-      atomicAdd(args.stats + 0, (unsigned long long)(clock64() - t_begin));
-      atomicAdd(args.stats + 1, (unsigned long long)t_wait_a);
-      atomicAdd(args.stats + 2, (unsigned long long)t_wait_w);
-      atomicAdd(args.stats + 3, 1ull);
-    }
+    umma_issuer<kBF16>(args, pc, lane);
   } else if (warp >= 4) {
     // ================================================================ epilogue warpgroups
     const int slot = ((warp - 4) >> 2) & 1;
@@ -796,9 +714,9 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           tile_in_smem = true;
           if constexpr (kPass != PASS_BWD) {
             constexpr int kP = kPass == PASS_TRAIN_FWD ? PASS_TRAIN_FWD : PASS_INFER;
-            float hs = 0.f;
-            lean_layer_epilogue<kBF16, true, kP, false, true>(taddr_base, 0, 8, slot_base + row_off, row7, gh, gm, valid, &hs);
-            out[3] = hs;          // + head_b[3] below
+            float hs[4] = {0.f, 0.f, 0.f, 0.f};
+            lean_layer_epilogue<kBF16, true, kP, false, true>(taddr_base, 0, 8, slot_base + row_off, row7, gh, gm, valid, hs);
+            out[3] = (hs[0] + hs[1]) + (hs[2] + hs[3]);          // + head_b[3] below
           }
         } else if (!general) {
           // lean path (the bias is already in the accumulator)

@@ -178,11 +178,11 @@ def test_ffmlp_presets_vs_reference(name):
     assert (out.depth.cpu().numpy() != g["depth"]).mean() <= 0.05
 
 
-@pytest.mark.parametrize("S", [1, 2, 8, 16, 32, 64, 128, 48, 100, 192, 256])
+@pytest.mark.parametrize("S", [1, 2, 3, 8, 16, 32, 64, 128, 48, 100, 129, 192, 256, 300])
 @pytest.mark.parametrize("R", [1, 37, 300])
 def test_ragged_shapes_vs_oracle(golden_nerf, R, S):
-    """Fused (S power of two <= 128) and two-kernel (other S) paths, tiles that straddle
-    rays, partial last tiles."""
+    """One fused launch for ANY samples-per-ray: rays aligned with the 128-row tiles (S | 128), rays that straddle
+    tiles (finished through per-ray partials by the last CTA to arrive), partial last tiles."""
     if S == 1:
         pytest.skip("the reference's argmax over an empty weights[:, :-1] is undefined for S=1")
     g, m = golden_nerf
@@ -202,7 +202,9 @@ def test_ragged_shapes_vs_oracle(golden_nerf, R, S):
     assert np.abs(c.cpu().numpy() - ref.color).max() <= PIX_TOL
     assert np.abs(a.cpu().numpy() - ref.alpha).max() <= PIX_TOL
     assert (dep.cpu().numpy() != ref.depth).mean() <= max(0.02, 1.5 / R)
+    before = _lib.launch_count()
     c2, a2, d2 = eng.net.render_samples(cuda(ref_s.positions), cuda(ref_s.view_directions), cuda(ref_s.t_values), True)
+    assert _lib.launch_count() - before == 1          # one kernel launch whatever S is
     assert torch.equal(c, c2) and torch.equal(a, a2) and torch.equal(dep, d2)
 
 

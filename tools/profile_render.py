@@ -1,5 +1,5 @@
 """Tiny driver for ncu: a few launches of the fused render kernel on synthetic rays.
-    ncu --set full --clock-control none --import-source on -k regex:ffn_render_kernel -s 2 -c 1 \
+    ncu --set full --clock-control none --import-source on -k regex:ffn_infer_kernel -s 2 -c 1 \
         -o gpurun_out/render python tools/profile_render.py --rays 262144 --iters 4
 """
 import argparse
@@ -45,8 +45,8 @@ if os.environ.get("FFN_STATS"):
     st = eng.net.debug_stats()
     tot, wa, ww, n = st[:4]
     if st[4] + st[5]:
-        print("epilogue warp 4 (per CTA, cycles): wait-acc %.0f  convert+store %.0f  front(enc) %.0f  back(composite) %.0f" % (
-            st[4] / n, st[5] / n, st[6] / n, st[7] / n))
+        print("epilogue warp 4 (per CTA, cycles): wait-acc %.0f  convert+store %.0f | aux warp 2: encode %.0f  composite %.0f  "
+              "wait-enc-free %.0f  wait-raw %.0f" % (st[4] / n, st[5] / n, st[6] / n, st[7] / n, st[30] / n, st[31] / n))
     # counters [8 + l]: summed over warp 4 (slot 0) of all 148 CTAs and over all launches
     tiles_per_slot = args.iters * R * S / 128 / 2
     print("epilogue cycles per tile and layer (acc-full -> A-ready):",
