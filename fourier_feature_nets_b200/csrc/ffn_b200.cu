@@ -612,15 +612,19 @@ static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int 
                                      cudaMemcpyDeviceToDevice, stream));
     g_loaded_gen = net->gen;
   }
+  size_t arena_bytes;
   if (pass == PASS_BWD) {
-    ka.wpack = net->d_wpack_bwd;
+    ka.wpack = net->d_wpack_bwd; arena_bytes = net->wpack_bwd_bytes;
     memcpy(ka.layers, net->layers_bwd, sizeof(net->layers_bwd));
     ka.num_layers = net->num_layers_bwd;
   } else {
-    ka.wpack = net->d_wpack;
+    ka.wpack = net->d_wpack; arena_bytes = net->wpack_bytes;
     memcpy(ka.layers, net->layers, sizeof(net->layers));
     ka.num_layers = net->num_layers;
   }
+  for (int i = 0; i < 4; ++i)
+    if (ffn_encode_rows128(&ka.wmap[i], ka.wpack, arena_bytes, 16 << i) != 0)
+      return fail("cuTensorMapEncodeTiled failed for the weight arena");
   ka.enc_kind = net->kind;
   ka.f_pos = net->f_pos; ka.f_view = net->f_view; ka.include_inputs = net->include_inputs;
   ka.use_view = net->use_view; ka.emb = net->emb; ka.ffm_a = net->d_ffm_a; ka.ffm_b = net->d_ffm_b;

@@ -146,6 +146,9 @@ struct KernelArgs {
   int32_t num_tiles;
   int32_t dz_tma;              // PASS_BWD: 1 = dz_out is written by TMA stores of the bf16 A tile (dz_map)
   int32_t sh_tma;              // PASS_TRAIN_FWD: 1 = save_h is written by TMA stores of the A tile (sh_map)
+  // the packed weight arena as rows of 128 bytes, one map per box height (16 / 32 / 64 / 128 rows = the half of a bias
+  // tile or weight K-chunk a CTA stages): 2-SM TMA loads that signal the leader CTA's barrier (ffn_pipeline.cuh)
+  alignas(64) CUtensorMap wmap[4];
   alignas(64) CUtensorMap dz_map;   // [n_dz][M][256] bf16, boxes of 64 columns x 32 rows, SWIZZLE_128B
   alignas(64) CUtensorMap sh_map;   // [n_save][M][256] operand dtype, same boxes
 };

@@ -337,8 +337,9 @@ ffn_infer_kernel(const __grid_constant__ KernelArgs args) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWStages; ++i) {
-      // rank 0's "full" barrier also collects rank 1's relay arrive; "empty" comes from one multicast commit
-      ptx::mbar_init(bar_w_full + 8 * i, cta_rank == 0 ? 2 : 1);
+      // the leader's "full" barrier: one arrive.expect_tx (its producer) + the bytes of both CTAs' loads;
+      // "empty" comes from one multicast commit
+      ptx::mbar_init(bar_w_full + 8 * i, 1);
       ptx::mbar_init(bar_w_empty + 8 * i, 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -385,10 +386,8 @@ ffn_infer_kernel(const __grid_constant__ KernelArgs args) {
 
   if (warp == 0) {
     weight_producer(args, pc, lane);
-  } else if (warp == 1 && cta_rank != 0) {
-    weight_relay(args, pc, lane);
   } else if (warp == 1) {
-    umma_issuer<kBF16>(args, pc, lane);
+    if (cta_rank == 0) umma_issuer<kBF16>(args, pc, lane);      // (rank 1's warp 1 idles)
   } else if (warp < 4) {
     // ================================================================ aux warp of slot (warp - 2)
     const int slot = warp - 2;

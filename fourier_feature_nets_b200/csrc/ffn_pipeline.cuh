@@ -2,7 +2,8 @@
 // ffn_render_kernel.cuh).  Per CTA of a 2-CTA cluster:
 //   warp 0           weight_producer   MY half of the rows of every pre-swizzled weight K-chunk (and bias tile) into a
 //                                      kWStages-deep shared-memory ring with the bulk-copy (TMA) engine
-//   warp 1, rank 1   weight_relay      "my half of this stage has landed" -> arrive on rank 0's "stage full" barrier
+//                                      (cp.async.bulk.tensor .cta_group::2: both CTAs' loads complete_tx on the
+//                                      LEADER's "stage full" barrier -- no relay hop through rank 1's warp 1)
 //   warp 1, rank 0   umma_issuer       tcgen05.mma.cta_group::2 kind::f16 (M = 256: 128 rows per CTA, N = 256 | 128,
 //                                      K = 16) for slot 0 then slot 1 of each layer; tcgen05.commit.multicast ->
 //                                      "stage free" and "accumulator full" barriers of BOTH CTAs
@@ -26,6 +27,10 @@ struct PipeCtx {
 
 __device__ __forceinline__ void weight_producer(const KernelArgs& args, const PipeCtx& pc, int lane) {
   uint32_t stage = 0, phase = 0;
+  // the leader's (rank 0) "stage full" barriers in shared::cluster space: both CTAs' loads complete_tx there
+  uint32_t full_leader[kWStages];
+#pragma unroll
+  for (int i = 0; i < kWStages; ++i) full_leader[i] = ptx::mapa_u32(pc.bar_w_full + 8 * i, 0u);
   for (int kp = 0; kp < pc.my_tiles; kp += 2) {
     const int nslots = min(2, pc.my_tiles - kp);
     for (int l = 0; l < pc.L; ++l) {
@@ -34,37 +39,23 @@ __device__ __forceinline__ void weight_producer(const KernelArgs& args, const Pi
       for (int s = 0; s < nslots; ++s) {
         // chunk -1 = the layer's bias tile (N x 32 B), then the weight K-chunks
         for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
-          ptx::mbar_wait(pc.bar_w_empty + 8 * stage, phase ^ 1u);
+          ptx::mbar_wait(pc.bar_w_empty + 8 * stage, phase ^ 1u);      // (multicast commit: both CTAs see "stage free")
           if (lane == 0) {
             const uint32_t nbytes = c < 0 ? (uint32_t)ld.n * 32u : bytes;
-            const uint8_t* src = c < 0 ? args.wpack + ld.bias_off : args.wpack + ld.w_offset + (size_t)c * bytes;
+            const uint32_t src_off = c < 0 ? ld.bias_off : ld.w_offset + (uint32_t)c * bytes;
             const uint32_t hb = nbytes >> 1;      // my half
             // my half of B's rows stays in MY shared memory; cta_group::2 reads the other half from the peer.
-            // Rows are contiguous in both the SW128 and the bias-tile layout.
-            ptx::mbar_arrive_expect_tx(pc.bar_w_full + 8 * stage, hb);
-            ptx::bulk_g2s(pc.smem_base + kSmemW + stage * kWStageBytes, src + pc.cta_rank * hb, hb,
-                          pc.bar_w_full + 8 * stage);
+            // Rows are contiguous in both the SW128 and the bias-tile layout: the arena is a 2-D tensor of 128-byte
+            // rows, my half a box of hb / 128 rows.  The leader expects the bytes of BOTH halves on its barrier.
+            const uint32_t rows = hb >> 7;
+            const int mi = rows >= 128 ? 3 : rows >= 64 ? 2 : rows >= 32 ? 1 : 0;
+            if (pc.cta_rank == 0) ptx::mbar_arrive_expect_tx(pc.bar_w_full + 8 * stage, nbytes);
+            ptx::tma_load_2d_pair(pc.smem_base + kSmemW + stage * kWStageBytes, &args.wmap[mi], 0,
+                                  (int)((src_off + pc.cta_rank * hb) >> 7), full_leader[stage]);
           }
           __syncwarp();
           if (++stage == kWStages) { stage = 0; phase ^= 1u; }
         }
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ void weight_relay(const KernelArgs& args, const PipeCtx& pc, int lane) {
-  uint32_t stage = 0, phase = 0;
-  for (int kp = 0; kp < pc.my_tiles; kp += 2) {
-    const int nslots = min(2, pc.my_tiles - kp);
-    for (int l = 0; l < pc.L; ++l) {
-      const LayerDesc& ld = args.layers[l];
-      const int nst = nslots * (ld.n_chunks + (ld.has_bias ? 1 : 0));
-      for (int i = 0; i < nst; ++i) {
-        ptx::mbar_wait(pc.bar_w_full + 8 * stage, phase);        // my half has landed in my shared memory
-        if (lane == 0) ptx::mbar_arrive_remote_relaxed(pc.bar_w_full + 8 * stage, 0u);
-        __syncwarp();
-        if (++stage == kWStages) { stage = 0; phase ^= 1u; }
       }
     }
   }
@@ -92,8 +83,8 @@ __device__ __forceinline__ void umma_issuer(const KernelArgs& args, const PipeCt
         uint32_t accumulate = ld.accumulate;
         for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
           t0 = prof ? clock64() : 0;
-          // completes on my half's bytes + the peer's relay arrive; the operands themselves are read through the
-          // async proxy, so a CTA-scope wait is enough (a cluster-scope acquire costs ~a fence each)
+          // completes on the bytes of both halves (mine and the peer's: 2-SM TMA loads signal this barrier); the
+          // operands themselves are read through the async proxy, so a CTA-scope wait is enough
           ptx::mbar_wait(pc.bar_w_full + 8 * stage, phase);
           if (prof) t_wait_w += clock64() - t0;
           ptx::tc_fence_after();

@@ -86,6 +86,21 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// 2-D tensor-map load issued by either CTA of a pair into ITS shared memory, completion (complete_tx) signalled on an
+// mbarrier that may live in the peer CTA (`mbar` is a shared::cluster address, e.g. from mapa): the leader's "stage
+// full" barrier collects the bytes of both halves without a relay hop
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const void* map, int c0, int c1, uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst_smem), "l"(map), "r"(c0), "r"(c1), "r"(mbar)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+
 // ---------------------------------------------------------------- TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),

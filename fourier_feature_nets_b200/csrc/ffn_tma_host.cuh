@@ -31,3 +31,17 @@ static int ffn_encode_bf16_3d(CUtensorMap* map, const void* ptr, long long rows,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
+
+// A byte arena as a 2-D tensor of 128-byte rows, boxes of `box_rows` rows, no swizzle (the arena already holds the
+// shared-memory image).  Returns 0 on success.
+static int ffn_encode_rows128(CUtensorMap* map, const void* ptr, size_t bytes, int box_rows) {
+  ffn_encode_tiled_fn encode = ffn_encode_fn();
+  if (!encode) return -1;
+  const cuuint64_t gdim[2] = {128, (cuuint64_t)(bytes / 128)};
+  const cuuint64_t gstr[1] = {128};
+  const cuuint32_t box[2] = {128, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return (int)encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
