@@ -415,7 +415,10 @@ def main():
     # all-reduce of the 595,844 gradients between backward and update (mean folded into ffn_clip_adam) ----------------
     def train_leg(rays_per_rank, label, steps=40, warm=8, S=128):
         torch.manual_seed(20080524)
-        tm = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True).to(dev)
+        if label == "tiny":       # configs[1]: train_tiny_nerf.py positional preset (train_tiny_nerf.py:75-88)
+            tm = ffn.PositionalFourierMLP(3, 4, 5.5).to(dev)
+        else:
+            tm = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True).to(dev)
         parallel.broadcast_parameters(tm)
         tr = ffn.FusedTrainer(tm, 5e-4)
         src = dev_bundles[W]
@@ -473,6 +476,8 @@ def main():
         return out
 
     leg("train", lambda: train_leg(1024, "train"))                    # weak: train_nerf.py:27 batch per rank
+    if world == 1:
+        leg("train_tiny", lambda: train_leg(1024, "tiny", S=64))
     if world > 1:
         leg("train_strong", lambda: train_leg(1024 // world, "strong"))   # strong: 1024 rays globally
 

@@ -124,6 +124,26 @@ _PERM_CACHE = {}
 _COLMAP_CACHE = {}
 
 
+def ffmlp_colmaps(E: int, device):
+    """Two int32[256] maps for the encoding slots a FourierFeatureMLP's training forward saves (see
+    ``RenderFFMLP.backward``): reference weight column of each saved column, -1 = padding.  E = 0: un-encoded MLP."""
+    key = ("ffmlp", E, str(device))
+    if key not in _COLMAP_CACHE:
+        def dst(mc):
+            if E:
+                e = mc >> 1
+                return (mc & 1) * E + e if e < E else -1
+            return mc if mc < 3 else -1
+        a = [dst(c) for c in range(256)]
+        if E:
+            b = [dst(320 + c) if c < 192 else dst(256 + c - 192) for c in range(256)]
+        else:
+            b = [dst(c - 192) if c >= 192 else -1 for c in range(256)]
+        _COLMAP_CACHE[key] = (torch.tensor(a, dtype=torch.int32, device=device),
+                              torch.tensor(b, dtype=torch.int32, device=device))
+    return _COLMAP_CACHE[key]
+
+
 def enc_colmap(num_freq: int, include_inputs: bool, first: int, device) -> torch.Tensor:
     """int32[64]: reference weight column (offset by ``first``) of each of OUR encoding-chunk columns, -1 = unused."""
     key = (num_freq, bool(include_inputs), first, str(device))
@@ -255,13 +275,6 @@ class RenderNeRF(torch.autograd.Function):
         return (None, None, None, *_as_param_grads(grads, params))
 
 
-def _positions_from_spec(spec, t_vals):
-    if spec["mode"] == "rays":
-        R, S = spec["R"], spec["S"]
-        return (spec["starts"].reshape(R, 1, 3) + t_vals.reshape(R, S, 1) * spec["directions"].reshape(R, 1, 3)).reshape(-1, 3)
-    return spec["positions"].reshape(-1, 3)
-
-
 class RenderFFMLP(torch.autograd.Function):
     """Same as :class:`RenderNeRF` for ``FourierFeatureMLP`` models (3 -> [256]*H -> 4, no view branch)."""
 
@@ -322,26 +335,26 @@ class RenderFFMLP(torch.autograd.Function):
             _lib._check(L.ffn_train_backward(net.handle, _p(d_raw), _p(save_mask), M, _p(dz), _lib._stream()),
                         "ffn_train_backward")
         H = len(lins) - 1
-        # layer 0 input: the encoding, recomputed in the reference's column order (fourier_feature_models.py:66-68)
-        pos = _positions_from_spec(ctx.spec, t_vals)
-        if model.b_values is None:
-            x0 = pos
-        else:
-            e = (math.pi * pos) @ model.b_values
-            x0 = torch.cat([model.a_values * e.cos(), model.a_values * e.sin()], dim=-1)
-        C0 = x0.shape[1]
-        Cpad = (C0 + 63) & ~63
-        x0p = torch.zeros((1, M, Cpad), dtype=torch.bfloat16, device=device)
-        x0p[0, :, :C0] = x0
+        # layer 0 input: the encoding rows the forward saved (OUR column order: column 2e + s of feature e, s = 0 cos /
+        # 1 sin) in the two extra slots of save_h -- slot H: encoding chunks 0..3, slot H + 1: columns [0,192) chunks
+        # 5..7, columns [192,256) chunk 4 (or the raw inputs of the un-encoded MLP); ffn_wgrad scatters the weight
+        # gradient to the reference's column order s*E + e (fourier_feature_models.py:66-68) through column maps
+        E = 0 if model.b_values is None else model.b_values.shape[1]
+        cm_a, cm_b = ffmlp_colmaps(E, device)
+        nch = (max(2 * E, 3) + 63) // 64
+        n1 = min(nch, 4) if E else 0
         flat, grads = _flat_grads(params, device)
         jobs = []
-        for w0 in range(0, Cpad, 256):          # layer 0 (fourier_feature_models.py:70-73), 256 input columns per job
-            n = min(256, Cpad - w0)
-            jobs.append(_wg_job(0, 2, 2, 0, w0, n, grads[0], w0, min(n, C0 - w0), None, grads[1] if w0 == 0 else None))
+        bias0 = grads[1]
+        if n1:
+            jobs.append(_wg_job(0, 2, 1, H, 0, 64 * n1, grads[0], 0, 64 * n1, cm_a, bias0))
+            bias0 = None
+        if nch > 4 or not E:
+            jobs.append(_wg_job(0, 2, 1, H + 1, 0, 256, grads[0], 0, 256, cm_b, bias0))
         for i in range(1, H):
             jobs.append(_wg_job(i, 2, 1, i - 1, 0, 256, grads[2 * i], 0, 256, None, grads[2 * i + 1]))
         with _lib.on_device(device):
-            _run_wgrad(L, [_wg_tensor(dz), _wg_tensor(save_h), _wg_tensor(x0p)], jobs)
+            _run_wgrad(L, [_wg_tensor(dz), _wg_tensor(save_h)], jobs)
             _head_grads(L, d_raw, 0, 4, save_h[H - 1], grads[2 * H], grads[2 * H + 1])    # final Linear 256 -> 4
         model.__dict__["_ffn_flat_grad"] = flat
         return (None, None, None, *_as_param_grads(grads, params))

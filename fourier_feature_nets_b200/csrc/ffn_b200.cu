@@ -94,6 +94,7 @@ struct ffn_net {
   uint8_t* d_wpack_bwd = nullptr;
   size_t wpack_bwd_bytes = 0;
   int n_save = 0, n_mask = 0, n_dz = 0;
+  int x0_slot = -1, x0_n1 = 0, x0_enc = 0, x0_n2 = 0;     // FourierFeatureMLP: where the forward saves the encoding
   int bwd_first_cols = 0, bwd_first_heads = 0, bwd_first_mask = 0, bwd_first_save = 0, bwd_sigma_chunk = 0;
 };
 static int build_nerf_backward(ffn_net* net, int L);

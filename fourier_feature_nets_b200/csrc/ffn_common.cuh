@@ -143,6 +143,11 @@ struct KernelArgs {
   int32_t bwd_first_mask;      //           sign-mask slot of that hidden layer
   int32_t bwd_first_save;      //           dz_out slot it is written to
   int32_t bwd_sigma_chunk;     //           1: d(sigma_raw) goes to column 0 of the encoding chunk
+  // PASS_TRAIN_FWD, FourierFeatureMLP / un-encoded MLP: the first layer's input (the encoding, our column order)
+  // is saved as two extra 256-column slots of save_h: slot x0_slot = encoding chunks 0..3 (features 0..127); slot
+  // x0_slot + 1 = columns [0,192): chunks 5..7 (features 160..255), columns [192,256): chunk 4 (features 128..159, or
+  // the raw inputs of the un-encoded MLP).  x0_slot < 0: nothing to save (NeRF: save_enc).
+  int32_t x0_slot, x0_n1, x0_enc, x0_n2;
   int32_t num_tiles;
   int32_t dz_tma;              // PASS_BWD: 1 = dz_out is written by TMA stores of the bf16 A tile (dz_map)
   int32_t sh_tma;              // PASS_TRAIN_FWD: 1 = save_h is written by TMA stores of the A tile (sh_map)

@@ -512,6 +512,14 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
         ptx::bulk_commit_group();
       }
     };
+    // this warp's 32 rows of ONE shared-memory chunk -> columns [col0, col0 + 64) of a save slot
+    auto tma_store_chunk = [&](const CUtensorMap* map, int chunk, int col0, long long tile_row0, int save_idx) {
+      if (lane == 0) {
+        ptx::tma_store_3d(map, slot_base + (uint32_t)chunk * kChunkBytesA + (uint32_t)(wq * 32) * 128u, col0,
+                          (int)tile_row0 + wq * 32, save_idx);
+        ptx::bulk_commit_group();
+      }
+    };
     bool pend = false;                              // a finished tile whose outputs are still to be written
     float p_out[4] = {0.f, 0.f, 0.f, 0.f}, p_tval = 0.f;
     int p_sidx = 0;
@@ -633,6 +641,9 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
         write_enc_ffmlp<kBF16>(slot_base + row_off, row7, px, py, pz, args.ffm_b, args.ffm_a,
                                args.emb, 0, 5);
       } else {
+        if constexpr (kPass == PASS_TRAIN_FWD) {
+          if (args.sh_tma) tma_tile_free();        // the previous tile's save of the encoding chunk
+        }
         write_enc_raw<kBF16>(enc_row_addr, row7, px, py, pz);
       }
       ptx::fence_proxy_async();
@@ -641,6 +652,13 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
       if (lane == 0) {
         if (kPair && cta_rank != 0) ptx::mbar_arrive_remote(my_a_ready, 0u);   // the issuer lives in rank 0
         else ptx::mbar_arrive(my_a_ready);
+      }
+      if constexpr (kPass == PASS_TRAIN_FWD) {
+        // FourierFeatureMLP / un-encoded MLP: the first layer's input rows leave as TMA stores of the tile just written
+        if (args.sh_tma && args.x0_slot >= 0) {
+          if (args.x0_n1 > 0) tma_store_tile(&args.sh_map, args.x0_n1, tile * kTileM, args.x0_slot);
+          if (args.x0_enc) tma_store_chunk(&args.sh_map, kEncChunk, 192, tile * kTileM, args.x0_slot + 1);
+        }
       }
 
       if constexpr (kPass == PASS_BWD) {
@@ -819,6 +837,9 @@ ffn_render_kernel(const __grid_constant__ KernelArgs args) {
           }
         }
         if constexpr (kPass == PASS_TRAIN_FWD) {
+          // second half of a wide encoding (features 160..255, act chunks 0..2) -> columns [0, 192) of slot x0_slot + 1
+          if (args.sh_tma && ld.epi == EPI_ENC_PART2 && args.x0_slot >= 0 && args.x0_n2 > 0)
+            tma_store_tile(&args.sh_map, args.x0_n2, tile * kTileM, args.x0_slot + 1);
           // the saved activations of this layer = this warp's 32 rows of the A tile it just wrote, in operand dtype
           if (args.sh_tma && ld.save_idx >= 0 && tile_in_smem && grp == 0 && !(args.dbg_flags & 32)) {
             if (l == L - 1) {

@@ -221,7 +221,20 @@ static int build_ffmlp_backward(ffn_net* net, int H) {
   const int tp = net->num_layers - H;
   for (int l = 0; l < net->num_layers; ++l) { net->layers[l].save_idx = -1; net->layers[l].mask_idx = -1; }
   for (int i = 0; i < H; ++i) { net->layers[i + tp].save_idx = (int8_t)i; net->layers[i + tp].mask_idx = (int8_t)i; }
-  net->n_save = H; net->n_mask = H; net->n_dz = H;
+  net->n_save = H + 2; net->n_mask = H; net->n_dz = H;
+  // the first layer's input (KernelArgs::x0_*): encoding chunks 0..3 -> slot H, chunk 4 and chunks 5..7 -> slot H + 1
+  {
+    const int cols = net->kind == ENC_FFMLP ? 2 * net->emb : 3;
+    const int nch_total = (cols + 63) / 64;
+    net->x0_slot = H;
+    if (net->kind == ENC_FFMLP) {
+      net->x0_n1 = std::min(nch_total, 4);
+      net->x0_enc = nch_total > 4 ? 1 : 0;
+      net->x0_n2 = nch_total > 5 ? nch_total - 5 : 0;
+    } else {
+      net->x0_n1 = 0; net->x0_enc = 1; net->x0_n2 = 0;      // raw inputs live in the encoding chunk
+    }
+  }
   net->bwd_first_cols = 256; net->bwd_first_heads = 4; net->bwd_first_mask = H - 1; net->bwd_first_save = H - 1;
   net->bwd_sigma_chunk = 0;
   net->trainable = true;
@@ -259,6 +272,7 @@ extern "C" int ffn_net_pack_backward(ffn_net_t* net, const float* const* weights
 }
 
 static void fill_train_common(ffn_net* net, KernelArgs& ka) {
+  ka.x0_slot = net->x0_slot; ka.x0_n1 = net->x0_n1; ka.x0_enc = net->x0_enc; ka.x0_n2 = net->x0_n2;
   ka.bwd_first_cols = net->bwd_first_cols; ka.bwd_first_heads = net->bwd_first_heads;
   ka.bwd_first_mask = net->bwd_first_mask; ka.bwd_first_save = net->bwd_first_save;
   ka.bwd_sigma_chunk = net->bwd_sigma_chunk;
@@ -299,6 +313,8 @@ extern "C" int ffn_train_forward(ffn_net_t* net, const float* positions, const f
   if (want_tma && ka.M < (1ll << 31) - 256 && (reinterpret_cast<uintptr_t>(save_h) & 15) == 0 &&
       ffn_encode_bf16_3d(&ka.sh_map, save_h, ka.M, 256, net->n_save, 32) == 0)
     ka.sh_tma = 1;
+  if (net->x0_slot >= 0 && !ka.sh_tma)
+    return fail("ffn_train_forward: FourierFeatureMLP training needs the TMA save path (16-byte aligned save_h, < 2^31 rows)");
   const bool fuse = fusable(S);
   ka.fused = fuse ? 1 : 0;
   if (fuse) { ka.rgb = color; ka.alpha = alpha; ka.depth = depth; }

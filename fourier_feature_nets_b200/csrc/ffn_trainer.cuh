@@ -23,7 +23,7 @@ struct ffn_trainer {
   cudaStream_t side = nullptr;           // the two CUDA-core head reductions run here, beside dgrad + wgrad
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   float grad_scale = 1.f;                // ffn_trainer_set_grad_scale: 1 / world size after a summing all-reduce
-  int* d_colmaps = nullptr;              // 3 x 64: pos encoding -> cols [0..), pos -> [256..), view -> [256..)
+  int* d_colmaps = nullptr;              // NeRF: 3 x 64 (pos -> cols [0..), pos -> [256..), view -> [256..)); FFMLP: 2 x 256
 };
 
 static size_t trainer_align(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -64,11 +64,10 @@ extern "C" void ffn_trainer_destroy(ffn_trainer_t* t);
 
 extern "C" int ffn_trainer_create(ffn_net_t* net, const ffn_trainer_desc_t* d, ffn_trainer_t** out) {
   if (!net || !d || !out) return fail("ffn_trainer_create: null argument");
-  if (!net->trainable || net->kind != ENC_NERF) return fail("ffn_trainer_create: NeRF nets only");
+  if (!net->trainable) return fail("ffn_trainer_create: this net has no training program");
   if (d->num_linear != net->num_linear || !d->weights || !d->biases || !d->weight_grad_offset || !d->bias_grad_offset ||
       !d->flat_grad || !d->exp_avg || !d->exp_avg_sq || d->flat_floats < 1)
     return fail("ffn_trainer_create: bad descriptor");
-  const int L = net->num_linear - 4;
   ffn_trainer* t = new ffn_trainer();
   t->net = net;
   t->num_linear = net->num_linear;
@@ -91,22 +90,38 @@ extern "C" int ffn_trainer_create(ffn_net_t* net, const ffn_trainer_desc_t* d, f
       return fail("ffn_trainer_create: gradient offsets outside the flat buffer");
     }
   }
-  (void)L;
   t->flat_grad = d->flat_grad; t->exp_avg = d->exp_avg; t->exp_avg_sq = d->exp_avg_sq; t->flat_floats = d->flat_floats;
-  // destination column of each of OUR encoding-chunk columns (6k + 2j + s <-> reference column s*3F + 3k + j,
-  // inputs 60 + j <-> 6F + j; nerf_model.py:97-109), -1 = padding
-  int h_cm[3 * 64];
-  for (int i = 0; i < 3 * 64; ++i) h_cm[i] = -1;
-  auto fill = [&](int* cm, int F, int first) {
-    for (int k = 0; k < F; ++k)
-      for (int j = 0; j < 3; ++j)
-        for (int s = 0; s < 2; ++s) cm[6 * k + 2 * j + s] = first + s * 3 * F + 3 * k + j;
-    if (net->include_inputs)
-      for (int j = 0; j < 3; ++j) cm[60 + j] = first + 6 * F + j;
-  };
-  fill(h_cm, net->f_pos, 0);
-  fill(h_cm + 64, net->f_pos, 256);
-  fill(h_cm + 128, net->f_view, 256);
+  int h_cm[3 * 256];
+  for (int i = 0; i < 3 * 256; ++i) h_cm[i] = -1;
+  if (net->kind == ENC_NERF) {
+    // destination column of each of OUR encoding-chunk columns (6k + 2j + s <-> reference column s*3F + 3k + j,
+    // inputs 60 + j <-> 6F + j; nerf_model.py:97-109), -1 = padding: maps [0,64) pos encoding -> cols [0..),
+    // [64,128) pos -> [256..) (skip layers), [128,192) view -> [256..)
+    auto fill = [&](int* cm, int F, int first) {
+      for (int k = 0; k < F; ++k)
+        for (int j = 0; j < 3; ++j)
+          for (int s = 0; s < 2; ++s) cm[6 * k + 2 * j + s] = first + s * 3 * F + 3 * k + j;
+      if (net->include_inputs)
+        for (int j = 0; j < 3; ++j) cm[60 + j] = first + 6 * F + j;
+    };
+    fill(h_cm, net->f_pos, 0);
+    fill(h_cm + 64, net->f_pos, 256);
+    fill(h_cm + 128, net->f_view, 256);
+  } else {
+    // FourierFeatureMLP (fourier_feature_models.py:66-68): our encoding column mc = 2e + s (s = 0: a cos, 1: a sin)
+    // <-> reference column s*E + e; the un-encoded MLP's inputs are columns 0..2.  Map A [0,256): the saved slot
+    // x0_slot (mc = c); map B [256,512): slot x0_slot + 1 (c < 192: mc = 320 + c, else mc = 256 + c - 192)
+    const int E = net->emb;
+    auto dst = [&](int mc) -> int {
+      if (net->kind == ENC_FFMLP) { const int e = mc >> 1; return e < E ? (mc & 1) * E + e : -1; }
+      return mc < 3 ? mc : -1;
+    };
+    for (int c = 0; c < 256; ++c) h_cm[c] = dst(c);
+    for (int c = 0; c < 256; ++c) {
+      if (net->kind == ENC_FFMLP) h_cm[256 + c] = c < 192 ? dst(320 + c) : dst(256 + c - 192);
+      else h_cm[256 + c] = c >= 192 ? dst(c - 192) : -1;
+    }
+  }
   if (cudaMalloc(&t->d_colmaps, sizeof(h_cm)) != cudaSuccess ||
       cudaMemcpy(t->d_colmaps, h_cm, sizeof(h_cm), cudaMemcpyHostToDevice) != cudaSuccess) {
     delete t;
@@ -161,25 +176,33 @@ extern "C" int ffn_trainer_backward(ffn_trainer_t* t, const float* positions, co
   CUDA_TRY(cudaMemsetAsync(t->flat_grad, 0, (size_t)t->flat_floats * sizeof(float), stream));
   // 3b. the CUDA-core heads need only d_raw and saved activations: they run on a side stream beside the dgrad chain
   // and ffn_wgrad (disjoint ranges of the flat buffer) and join before this call returns.
-  // opacity_out reads trunk output L-1, color_out the 128 hidden_view channels (slot L+1)
+  const bool nerf = net->kind == ENC_NERF;
+  const int act_fp16 = net->bf16 ? 0 : 1;      // the forward saves activations / encodings in its operand dtype
   {
-    const int act16 = net->bf16 ? 0 : 1;
     const uint8_t* sh = (const uint8_t*)w.save_h;
     const size_t slot = (size_t)M * 256 * 2;
     CUDA_TRY(cudaEventRecord(t->ev_fork, stream));
     CUDA_TRY(cudaStreamWaitEvent(t->side, t->ev_fork, 0));
-    if (ffn_head_wgrad(w.d_raw, 3, 1, sh + (size_t)(L - 1) * slot, M, t->flat_grad + t->gw_off[L],
-                       t->flat_grad + t->gb_off[L], 256, act16, t->side))
-      return 1;
-    if (ffn_head_wgrad(w.d_raw, 0, 3, sh + (size_t)(L + 1) * slot, M, t->flat_grad + t->gw_off[L + 3],
-                       t->flat_grad + t->gb_off[L + 3], 128, act16, t->side))
-      return 1;
+    if (nerf) {
+      // opacity_out reads trunk output L-1, color_out the 128 hidden_view channels (slot L+1)
+      if (ffn_head_wgrad(w.d_raw, 3, 1, sh + (size_t)(L - 1) * slot, M, t->flat_grad + t->gw_off[L],
+                         t->flat_grad + t->gb_off[L], 256, act_fp16, t->side))
+        return 1;
+      if (ffn_head_wgrad(w.d_raw, 0, 3, sh + (size_t)(L + 1) * slot, M, t->flat_grad + t->gw_off[L + 3],
+                         t->flat_grad + t->gb_off[L + 3], 128, act_fp16, t->side))
+        return 1;
+    } else {
+      // the final Linear 256 -> 4 (fourier_feature_models.py:77) reads the last hidden activation (slot H-1)
+      const int H = net->num_linear - 1;
+      if (ffn_head_wgrad(w.d_raw, 0, 4, sh + (size_t)(H - 1) * slot, M, t->flat_grad + t->gw_off[H],
+                         t->flat_grad + t->gb_off[H], 256, act_fp16, t->side))
+        return 1;
+    }
     CUDA_TRY(cudaEventRecord(t->ev_join, t->side));
   }
   if (ffn_net_pack_backward(net, t->w.data(), stream_)) return 1;
   if (ffn_train_backward(net, w.d_raw, w.save_mask, M, w.dz, stream_)) return 1;
   // 6. every weight / bias gradient of the MMA layers into the flat buffer
-  const int act_fp16 = net->bf16 ? 0 : 1;      // the forward saves activations / encodings in its operand dtype
   ffn_wgrad_tensor_t tens[3] = {{w.dz, M, 256, net->n_dz, 0}, {w.save_h, M, 256, net->n_save, act_fp16},
                                 {w.save_enc, M, 64, 2, act_fp16}};
   ffn_wgrad_job_t jobs[ffn::kWgMaxJobs];
@@ -192,18 +215,30 @@ extern "C" int ffn_trainer_backward(ffn_trainer_t* t, const float* positions, co
     J.dst = t->flat_grad + t->gw_off[lin]; J.dst_stride = t->w_in[lin]; J.dst_col0 = 0; J.dst_cols = dst_cols;
     J.colmap = cm; J.bias_dst = bias ? t->flat_grad + t->gb_off[lin] : nullptr;
   };
-  for (int i = 0; i < L; ++i) {            // trunk (nerf_model.py:111-116)
-    if (i == 0) {
-      job(0, 2, 2, 0, 64, 0, 64, t->d_colmaps, true);
-    } else {
-      job(i, 2, 1, i - 1, 256, i, 256, nullptr, true);
-      if (t->w_in[i] > 256) job(i, 2, 2, 0, 64, i, 64, t->d_colmaps + 64, false);     // skip layer: [h | enc_p]
+  int n_tens = 3;
+  if (nerf) {
+    for (int i = 0; i < L; ++i) {            // trunk (nerf_model.py:111-116)
+      if (i == 0) {
+        job(0, 2, 2, 0, 64, 0, 64, t->d_colmaps, true);
+      } else {
+        job(i, 2, 1, i - 1, 256, i, 256, nullptr, true);
+        if (t->w_in[i] > 256) job(i, 2, 2, 0, 64, i, 64, t->d_colmaps + 64, false);     // skip layer: [h | enc_p]
+      }
     }
+    job(L, 2, 1, L - 1, 256, L + 1, 256, nullptr, true);                 // bottleneck (nerf_model.py:119)
+    job(L + 1, 1, 1, L, 256, L + 2, 256, nullptr, true);                 // hidden_view (nerf_model.py:121-122)
+    job(L + 1, 1, 2, 1, 64, L + 2, 64, t->d_colmaps + 128, false);
+  } else {
+    // FourierFeatureMLP (fourier_feature_models.py:70-77): hidden layer i reads h_i = slot i-1; layer 0 reads the
+    // encoding saved in slots x0_slot / x0_slot + 1 (our column order -> the reference's through the column maps)
+    n_tens = 2;
+    const int H = net->num_linear - 1;
+    bool bias0 = true;
+    if (net->x0_n1 > 0) { job(0, 2, 1, net->x0_slot, 64 * net->x0_n1, 0, 64 * net->x0_n1, t->d_colmaps, bias0); bias0 = false; }
+    if (net->x0_enc || net->x0_n2 > 0) job(0, 2, 1, net->x0_slot + 1, 256, 0, 256, t->d_colmaps + 256, bias0);
+    for (int i = 1; i < H; ++i) job(i, 2, 1, i - 1, 256, i, 256, nullptr, true);
   }
-  job(L, 2, 1, L - 1, 256, L + 1, 256, nullptr, true);                 // bottleneck (nerf_model.py:119)
-  job(L + 1, 1, 1, L, 256, L + 2, 256, nullptr, true);                 // hidden_view (nerf_model.py:121-122)
-  job(L + 1, 1, 2, 1, 64, L + 2, 64, t->d_colmaps + 128, false);
-  if (ffn_wgrad(tens, 3, jobs, nj, stream_)) return 1;
+  if (ffn_wgrad(tens, n_tens, jobs, nj, stream_)) return 1;
   CUDA_TRY(cudaStreamWaitEvent(stream, t->ev_join, 0));      // 7. join the head reductions
   return 0;
 }

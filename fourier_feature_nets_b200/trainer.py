@@ -45,21 +45,22 @@ def _bind(L):
 
 
 def supported(model) -> bool:
-    if getattr(model, "_ffn_kind", None) != "nerf" or not _engine.supported(model):
+    if getattr(model, "_ffn_kind", None) not in ("nerf", "fourier") or not _engine.supported(model):
         return False
     params = [q for lin in _engine._linear_list(model) for q in (lin.weight, lin.bias)]
     return all(q.is_cuda and q.dtype == torch.float32 and q.is_contiguous() and q.requires_grad for q in params)
 
 
 class FusedTrainer:
-    """Clip + Adam training of a NeRF on ray batches against ground-truth tables, two C calls per step.
+    """Clip + Adam training of a NeRF or FourierFeatureMLP (3 -> [256] * n -> 4) on ray batches against ground-truth tables, two C calls per step.
 
     ``param_groups`` mimics ``torch.optim.Optimizer`` far enough for ``exponential_lr_decay``."""
 
     def __init__(self, model, lr: float, weight_decay: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8,
                  clip_value: float = 0.1, max_norm: float = 0.1):
         if not supported(model):
-            raise _lib.FFNError("FusedTrainer needs a float32 NeRF on a CUDA device")
+            raise _lib.FFNError("FusedTrainer needs a float32 NeRF / FourierFeatureMLP of a shape the fused kernels "
+                                "cover, on a CUDA device")
         self.model = model
         self.device = next(model.parameters()).device
         self.param_groups = [dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, clip_value=clip_value,

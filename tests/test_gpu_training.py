@@ -347,10 +347,60 @@ def test_fused_trainer_equals_the_autograd_step():
     trainer.update()
 
 
+@pytest.mark.parametrize("preset", ["mlp", "basic", "positional", "gaussian"])
+def test_fused_trainer_covers_the_fourier_feature_presets(preset):
+    """BASELINE.json configs[1]: the C trainer (two calls per step) on train_tiny_nerf.py's presets.  The forward saves
+    the first layer's input (the encoding) as two extra slots of the activation tensor -- no eager re-encoding --
+    and ffn_wgrad scatters its weight gradient to the reference's column order: same gradients as the autograd path
+    (same kernels, 1e-4), which itself is checked against fp32 autograd above; same update."""
+    from fourier_feature_nets_b200.autograd import MSELoss
+    def make():
+        torch.manual_seed(4)
+        m = {"mlp": lambda: ffn.MLP(3, 4), "basic": lambda: ffn.BasicFourierMLP(3, 4),
+             "positional": lambda: ffn.PositionalFourierMLP(3, 4, 5.5),
+             "gaussian": lambda: ffn.GaussianFourierMLP(3, 4, 3.14)}[preset]()
+        with torch.no_grad():
+            for name, p in m.named_parameters():
+                if p.requires_grad and name.endswith("weight"):
+                    p.mul_(1.5)
+        return m.to(DEV)
+    a_model, b_model = make(), make()
+    R, S, N = 200, 64, 3000
+    g = torch.Generator(device=DEV).manual_seed(5)
+    gt_c = torch.rand((N, 3), device=DEV, generator=g)
+    gt_a = (torch.rand((N,), device=DEV, generator=g) > 0.3).float()
+    rc = ffn.Raycaster(a_model)
+    ordered = [q for lin in a_model.layers for q in (lin.weight, lin.bias)]
+    opt = ffn.ClipAdam(ordered, 5e-4, clip_value=0.1, max_norm=0.1)
+    trainer = ffn.FusedTrainer(b_model, 5e-4, clip_value=0.1, max_norm=0.1)
+    lin = torch.linspace(0, 1, S).to(DEV)
+    for step in range(2):
+        bundle = make_batch(R, S, seed=step).to(DEV)
+        idx = torch.randint(0, N, (R,), device=DEV, generator=g)
+        bundle = ffn.RayBundle(bundle.starts, bundle.directions, bundle.near, bundle.far, idx, S, True, bundle.jitter)
+        opt.zero_grad()
+        out = rc.render(bundle, True)
+        loss_a = MSELoss.apply(out.color, out.alpha, gt_c, gt_a, idx, 0.1)
+        loss_a.backward()
+        before = _lib.launch_count()
+        loss_b = trainer.backward(bundle, gt_c, gt_a, 0.1, lin)
+        assert _lib.launch_count() - before >= 6
+        assert abs(loss_a.item() - loss_b.item()) <= 1e-6 * max(1.0, abs(loss_a.item()))
+        for la, lb in zip(a_model.layers, b_model.layers):
+            for pa, pb in ((la.weight, lb.weight), (la.bias, lb.bias)):
+                da, db = pa.grad.flatten().double(), pb.grad.flatten().double()
+                assert da.norm() > 0 and ((da - db).norm() / (da.norm() + 1e-30)).item() <= 1e-4, (preset, step)
+                pa.grad.copy_(pb.grad)
+        opt.step()
+        trainer.update()
+        for pa, pb in zip(ordered, [q for lin in b_model.layers for q in (lin.weight, lin.bias)]):
+            assert torch.equal(pa, pb), (preset, step)
+
+
 @pytest.mark.parametrize("preset", ["positional", "gaussian"])
 def test_fit_fourier_feature_mlp_on_the_gpu(tmp_path, preset):
     """BASELINE.json configs[1] (train_tiny_nerf.py): a FourierFeatureMLP preset through Raycaster.fit on the GPU --
-    training kernels under autograd, fused loss, ClipAdam (the C trainer covers NeRF models only)."""
+    the C trainer (FusedTrainer), fused loss, clip + Adam."""
     import subprocess
     import sys
     from conftest import ROOT
