@@ -68,6 +68,14 @@ class FourierFeatureMLP(nn.Module):
             return eng.net.mlp_forward(inputs.reshape(-1, 3), None).reshape(*inputs.shape[:-1], 4)
         return self.forward_torch(inputs)
 
+    def __getstate__(self):
+        """``copy.deepcopy`` / pickling: the C handles bound to this instance (engine, trainer, flat gradient buffer)
+        stay behind; the copy builds its own on first use."""
+        state = self.__dict__.copy()
+        for key in [k for k in state if k.startswith("_ffn_")]:
+            del state[key]
+        return state
+
     def save(self, path: str):
         state_dict = self.state_dict()
         state_dict["type"] = "fourier"

@@ -89,6 +89,14 @@ class NeRF(nn.Module):
             return eng.net.mlp_forward(position.reshape(-1, 3), view.reshape(-1, 3))
         return self.forward_torch(position, view)
 
+    def __getstate__(self):
+        """``copy.deepcopy`` / pickling: the C handles bound to this instance (engine, trainer, flat gradient buffer)
+        stay behind; the copy builds its own on first use."""
+        state = self.__dict__.copy()
+        for key in [k for k in state if k.startswith("_ffn_")]:
+            del state[key]
+        return state
+
     def save(self, path: str):
         """Same ``.pt`` layout as nerf_model.py:126-135."""
         state_dict = self.state_dict()

@@ -167,6 +167,56 @@ class Raycaster(nn.Module):
         return RenderResult(torch.cat(colors).cpu().numpy(), torch.cat(alphas).cpu().numpy(),
                             torch.cat(depths).cpu().numpy() if include_depth else None)
 
+    def render_stream(self, sampler: RaySampler, index_batches, include_depth: bool = False, step=None):
+        """Generator over ``RenderResult``s (numpy) of consecutive ray-index batches, host buffers in and out:
+        ``sampler.sample(idx, step)`` -> host->device copy -> fused kernel -> device->host copy of the pixels, with the
+        stages of neighbouring batches overlapped -- while the GPU renders batch i the host gathers batch i + 1 from the
+        ray tables (into pinned staging when the sampler has it: ``RaySampler.enable_pinned_staging``) and unpacks the
+        pixels of batch i - 1.  Equivalent to ``[self.render(sampler.sample(b, step).to(device), d).numpy() for b in
+        index_batches]`` (what ``batched_render`` does per frame, ray_caster.py:122-131), minus the idle gaps."""
+        device = next(self.model.parameters()).device
+        if device.type != "cuda":
+            for idx in index_batches:
+                with torch.no_grad():
+                    yield self.render(sampler.sample(idx, step).to(device), include_depth).numpy()
+            return
+        pending = None      # (event, pinned color, alpha, depth)
+        pool = []           # two sets of pinned result buffers, rotating
+
+        def pinned(i, n):
+            while len(pool) <= i:
+                pool.append(None)
+            if pool[i] is None or pool[i][0].shape[0] < n:
+                pool[i] = (torch.empty((n, 3), dtype=torch.float32).pin_memory(),
+                           torch.empty((n,), dtype=torch.float32).pin_memory(),
+                           torch.empty((n,), dtype=torch.float32).pin_memory())
+            return pool[i]
+
+        def unpack(p):
+            ev, n, bufs = p
+            ev.synchronize()
+            return RenderResult(bufs[0][:n].numpy().copy(), bufs[1][:n].numpy().copy(),
+                                bufs[2][:n].numpy().copy() if include_depth else None)
+
+        with torch.no_grad():
+            for i, idx in enumerate(index_batches):
+                bundle = sampler.sample(idx, step)                      # host work, overlaps the previous launch
+                pred = self.render(bundle.to(device, non_blocking=True), include_depth)
+                n = pred.color.shape[0]
+                bufs = pinned(i & 1, n)
+                bufs[0][:n].copy_(pred.color, non_blocking=True)
+                bufs[1][:n].copy_(pred.alpha, non_blocking=True)
+                if include_depth:
+                    bufs[2][:n].copy_(pred.depth, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                if pending is not None:
+                    yield unpack(pending)
+                pending = (ev, n, bufs)
+            if pending is not None:
+                yield unpack(pending)
+            self.check_nan()
+
     def render_image(self, sampler: RaySampler, index: int, batch_size: int,
                      color_space="RGB") -> np.ndarray:
         """Render camera ``index % num_cameras`` to an (H,W,3) uint8 image."""

@@ -371,3 +371,23 @@ def test_batched_render_draws_independent_jitter_per_batch():
     np.testing.assert_array_equal(whole, halves)               # batching does not change the draws ...
     assert np.abs(halves[:n] - halves[n:]).max() > 1e-4         # ... and identical rays in different batches differ
     assert np.abs(halves[0] - halves[1]).max() > 1e-5
+
+
+def test_render_stream_pipeline_on_the_gpu(golden_nerf):
+    """Raycaster.render_stream with host ray tables + pinned staging: same pixels as the step-by-step calls, results
+    stay valid after later batches have reused the pinned buffers."""
+    g, m = golden_nerf
+    from bench import BOUNDS, make_cameras
+    s = ffn.RaySampler(BOUNDS, make_cameras(ffn, 2, 64), 32, stratified=False)
+    s.enable_pinned_staging(3000)
+    valid = torch.nonzero(s.valid_mask).flatten()
+    batches = [valid[i * 1000:(i + 1) * 1000 + 37 * i] for i in range(5)]
+    rc = ffn.Raycaster(m)
+    before = _lib.launch_count()
+    got = list(rc.render_stream(s, batches, True))
+    assert _lib.launch_count() - before == len(batches)
+    with torch.no_grad():
+        for r, b in zip(got, batches):
+            want = rc.render(s.sample(b, None).to(DEV), True).numpy()
+            np.testing.assert_array_equal(r.color, want.color)
+            np.testing.assert_array_equal(r.depth, want.depth)

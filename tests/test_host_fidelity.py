@@ -163,3 +163,29 @@ def test_ray_offset_follows_subsets():
     t0, t1 = b.subset(range(0, 4)).t_values, b.subset(range(4, 8)).t_values
     assert not torch.equal(t0, t1)
     assert torch.equal(b.subset(range(4, 8)).t_values, t1)
+
+
+def test_render_stream_equals_batchwise_render():
+    """Raycaster.render_stream (pipelined host-in / host-out API) yields, in order, exactly what
+    ``render(sampler.sample(idx).to(device)).numpy()`` returns per batch (here on the CPU definition; the CUDA
+    pipeline is covered by tests/test_gpu_parity.py)."""
+    res = 24
+    f = .5 * res / np.tan(.5 * 40 * np.pi / 180)
+    K = np.array([[f, 0, res / 2], [0, f, res / 2], [0, 0, 1]], np.float32)
+    E = ffn.utils.look_at_extrinsics(np.array([0.5, 1.0, -3.8]), np.array([0, 1.0, 0])).astype(np.float32)
+    cam = ffn.CameraInfo.create("c", ffn.Resolution(res, res), K, E)
+    s = ffn.RaySampler(np.diag([2, 2, 2, 1]).astype(np.float32), [cam], 8)
+    torch.manual_seed(0)
+    rc = ffn.Raycaster(ffn.NeRF(2, 32, 3, 4, 2, 2, [1], True))
+    valid = torch.nonzero(s.valid_mask).flatten()
+    batches = [valid[:100], valid[100:250], valid[250:257]]
+    got = list(rc.render_stream(s, batches, True))
+    assert len(got) == 3
+    with torch.no_grad():
+        for g, b in zip(got, batches):
+            want = rc.render(s.sample(b, None), True).numpy()
+            np.testing.assert_array_equal(g.color, want.color)
+            np.testing.assert_array_equal(g.alpha, want.alpha)
+            np.testing.assert_array_equal(g.depth, want.depth)
+    assert [len(g.alpha) for g in got] == [100, 150, 7]
+    assert list(rc.render_stream(s, [], True)) == []
