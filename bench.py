@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--operand", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--cpu-rays", type=int, default=8192, help="rays of the parity sample")
     ap.add_argument("--ref-rays", type=int, default=16384, help="rays per step of the timed CPU reference sample")
-    ap.add_argument("--legs", default="all", help="comma list of extra legs: train,frame,spp,cpu,torchgpu,parity | all | none")
+    ap.add_argument("--legs", default="all", help="comma list of extra legs: train,frame,spp,precise,cpu,torchgpu,parity | all | none")
     return ap.parse_args()
 
 
@@ -282,7 +282,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
-    legs = set("train,frame,spp,cpu,torchgpu,parity".split(",")) if args.legs == "all" else \
+    legs = set("train,frame,spp,precise,cpu,torchgpu,parity".split(",")) if args.legs == "all" else \
         set(x for x in args.legs.split(",") if x and x != "none")
 
     R, K, W = args.rays, args.steps, args.warmup
@@ -550,6 +550,32 @@ def main():
             return out
 
         leg("spp", spp_leg)
+
+        # ---- the precise operand mode (fp16 hi + residual split, three UMMAs per product): fp32-grade pixels --------
+        def precise_leg():
+            import copy
+            n = 1 << 17
+            src = dev_bundles[W]
+            pm = copy.deepcopy(model)
+            pm.ffn_operand = "fp16x3"
+            prc = ffn.Raycaster(pm)
+            b = ffn.RayBundle(src.starts[:n], src.directions[:n], src.near[:n], src.far[:n], src.rays[:n], SAMPLES, True,
+                              None, seed=5)
+            with torch.no_grad():
+                prc.render(b, True)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    prc.render(b, True)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            return {"rays_s": round(n / ms * 1e3), "operand": "fp16x3",
+                    "frac_tensor_algorithmic": round(n * SAMPLES * FLOP_PER_SAMPLE / (ms / 1e3) / 1e12 / pk["tensor"], 3),
+                    "frac_tensor_executed": round(3 * n * SAMPLES * FLOP_PER_SAMPLE / (ms / 1e3) / 1e12 / pk["tensor"], 3)}
+
+        leg("precise", precise_leg)
 
         # ---- the real reference on the host cores (bounded sample) and on this GPU ---------------------------------
         ref_state = {k: v.detach().cpu() for k, v in model.state_dict().items()}

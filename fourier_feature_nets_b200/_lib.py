@@ -24,6 +24,7 @@ FFN_MAX_LAYERS = 16
 FFN_MAX_FREQS = 10
 OPERAND_FP16 = 0
 OPERAND_BF16 = 1
+OPERAND_FP16X3 = 2      # NeRF inference: hi + residual split of every operand, three UMMAs per product
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

@@ -14,6 +14,7 @@
 #include "ffn_common.cuh"
 #include "ffn_render_kernel.cuh"
 #include "ffn_infer_kernel.cuh"
+#include "ffn_infer_x3_kernel.cuh"
 
 using namespace ffn;
 
@@ -65,6 +66,7 @@ struct BwdPackArgs {
 struct ffn_net {
   int kind = 0;             // ENC_*
   int bf16 = 0;
+  int precise = 0;          // FFN_OPERAND_FP16X3: the arena holds a second (residual) weight image behind the first
   int num_linear = 0;
   int use_view = 0;
   int f_pos = 0, f_view = 0, include_inputs = 0, emb = 0;
@@ -125,7 +127,8 @@ struct PackArgs {
 
 // one thread = one 16-byte unit (8 consecutive K elements of one weight row) of the
 // K-major SWIZZLE_128B image the UMMA B descriptor expects
-template <bool kBF16>
+// kLo: the fp16 residual image  fp16(w - fp32(fp16(w)))  of the fp16x3 mode
+template <bool kBF16, bool kLo = false>
 __global__ void pack_weights_kernel(const __grid_constant__ PackArgs pa, const int* __restrict__ colmap,
                                     uint8_t* __restrict__ out) {
   const int l = blockIdx.y;
@@ -144,6 +147,7 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs pa, const i
     for (int e = 0; e < 8; ++e) {
       const int col = cm[e];
       v[e] = col >= 0 ? w[(size_t)row * inf + col] : 0.f;
+      if constexpr (kLo) v[e] -= __half2float(__float2half_rn(v[e]));
     }
     uint4 pk;
     pk.x = ptx::pack2<kBF16, false>(v[0], v[1]);
@@ -324,8 +328,8 @@ static int finalize_net(ffn_net* net) {
     if (has_bias) off += (uint32_t)net->layers[l].n * 32u;
   }
   net->wpack_bytes = off;
-  CUDA_TRY(cudaMalloc(&net->d_wpack, net->wpack_bytes));
-  CUDA_TRY(cudaMemset(net->d_wpack, 0, net->wpack_bytes));
+  CUDA_TRY(cudaMalloc(&net->d_wpack, net->wpack_bytes * (net->precise ? 2 : 1)));
+  CUDA_TRY(cudaMemset(net->d_wpack, 0, net->wpack_bytes * (net->precise ? 2 : 1)));
   CUDA_TRY(cudaMalloc(&net->d_colmap, net->colmap_host.size() * sizeof(int)));
   CUDA_TRY(cudaMemcpy(net->d_colmap, net->colmap_host.data(), net->colmap_host.size() * sizeof(int),
                       cudaMemcpyHostToDevice));
@@ -373,6 +377,7 @@ extern "C" int ffn_nerf_create(const ffn_nerf_desc_t* d, ffn_net_t** out) {
   ffn_net* net = new ffn_net();
   net->kind = ENC_NERF;
   net->bf16 = d->operand_dtype == FFN_OPERAND_BF16;
+  net->precise = d->operand_dtype == FFN_OPERAND_FP16X3;
   net->use_view = 1;
   net->f_pos = Fp; net->f_view = Fv; net->include_inputs = d->include_inputs;
   net->num_linear = L + 4;
@@ -442,6 +447,7 @@ extern "C" int ffn_ffmlp_create(int32_t num_hidden, int32_t num_channels, int32_
                                 const float* a_host, const float* b_host, int32_t operand_dtype,
                                 ffn_net_t** out) {
   if (!out) return fail("ffn_ffmlp_create: null argument");
+  if (operand_dtype == FFN_OPERAND_FP16X3) return fail("ffn_ffmlp_create: the fp16x3 mode covers NeRF handles only");
   if (num_channels != 256) return fail("ffn_ffmlp_create: num_channels must be 256");
   if (num_hidden < 1 || num_hidden + 1 > kMaxMmaLayers) return fail("ffn_ffmlp_create: 1..11 hidden layers");
   const bool encoded = b_host != nullptr;
@@ -573,6 +579,10 @@ extern "C" int ffn_net_pack(ffn_net_t* net, const float* const* weights, const f
   if (net->bf16) pack_const_kernel<true><<<1, 256, 0, stream>>>(pa, net->d_cparams, net->d_wpack);
   else pack_const_kernel<false><<<1, 256, 0, stream>>>(pa, net->d_cparams, net->d_wpack);
   g_launches += 2;
+  if (net->precise) {
+    pack_weights_kernel<false, true><<<grid, 256, 0, stream>>>(pa, net->d_colmap, net->d_wpack + net->wpack_bytes);
+    g_launches += 1;
+  }
   CUDA_TRY(cudaGetLastError());
   net->gen = g_gen.fetch_add(1);
   net->packed = true;
@@ -619,7 +629,8 @@ static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int 
     memcpy(ka.layers, net->layers_bwd, sizeof(net->layers_bwd));
     ka.num_layers = net->num_layers_bwd;
   } else {
-    ka.wpack = net->d_wpack; arena_bytes = net->wpack_bytes;
+    ka.wpack = net->d_wpack; arena_bytes = net->wpack_bytes * (net->precise ? 2 : 1);
+    ka.wpack_lo_off = (uint32_t)net->wpack_bytes;
     memcpy(ka.layers, net->layers, sizeof(net->layers));
     ka.num_layers = net->num_layers;
   }
@@ -653,7 +664,16 @@ static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int 
   } else if (pass == PASS_TRAIN_FWD) {
     if (net->bf16 ? launch_variant<true, PASS_TRAIN_FWD>(cfg, ka) : launch_variant<false, PASS_TRAIN_FWD>(cfg, ka)) return 1;
   } else {
-    if (net->bf16 ? launch_infer<true>(cfg, ka) : launch_infer<false>(cfg, ka)) return 1;
+    if (net->precise && ka.dbg_layer < 0) {
+      static bool x3_attr = false;
+      if (!x3_attr) {
+        CUDA_TRY(cudaFuncSetAttribute(ffn_infer_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+        x3_attr = true;
+      }
+      CUDA_TRY(cudaLaunchKernelEx(&cfg, ffn_infer_x3_kernel, ka));
+    } else if (net->bf16 ? launch_infer<true>(cfg, ka) : launch_infer<false>(cfg, ka)) {
+      return 1;
+    }
   }
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());

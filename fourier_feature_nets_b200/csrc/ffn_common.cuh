@@ -93,6 +93,7 @@ struct ConstParams {
 
 struct KernelArgs {
   const uint8_t* wpack;
+  uint32_t wpack_lo_off;       // fp16x3 mode: byte offset of the residual ("lo") weight image inside the arena
   LayerDesc layers[kMaxMmaLayers];
   int32_t num_layers;
   int32_t enc_kind;

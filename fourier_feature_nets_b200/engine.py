@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 
-_OPERAND = {"fp16": _lib.OPERAND_FP16, "bf16": _lib.OPERAND_BF16}
+_OPERAND = {"fp16": _lib.OPERAND_FP16, "bf16": _lib.OPERAND_BF16, "fp16x3": _lib.OPERAND_FP16X3}
 DEFAULT_OPERAND = "fp16"
 
 

@@ -37,6 +37,10 @@ extern "C" {
  * heads and compositing are always float32) */
 #define FFN_OPERAND_FP16 0
 #define FFN_OPERAND_BF16 1
+/* NeRF handles, inference entry points: every operand split into fp16 high + residual parts, three UMMAs per product
+ * (x_hi w_hi + x_lo w_hi + x_hi w_lo, fp32 accumulate): fp32-grade pixels at ~1/6 of the fp16 throughput.  Training entry
+ * points of such a handle run with fp16 operands. */
+#define FFN_OPERAND_FP16X3 2
 
 #define FFN_MAX_LAYERS 16
 #define FFN_MAX_FREQS 10
@@ -92,7 +96,10 @@ int ffn_mlp_forward(ffn_net_t* net, const float* positions, const float* views, 
 /* Raycaster.render on materialised RaySamples (ray_caster.py:48-93):
  * positions (R,S,3), view_directions (R,S,3) or NULL, t_values (R,S)
  * -> color (R,3), alpha (R), depth (R) or NULL.  nan_flag: device int, OR-ed with 1 when a
- * NaN colour/opacity is produced (the reference's asserts at ray_caster.py:73-74). */
+ * NaN colour/opacity is produced (the reference's asserts at ray_caster.py:73-74).
+ * ONE kernel launch for any num_samples >= 1 (ffn_render_samples / _rays / _rays_t): when 128 % num_samples != 0 rays
+ * straddle the kernel's 128-sample tiles and are finished through per-ray partials in a scratch buffer owned by the
+ * handle (grown on demand: 32 * ((S + 126) / 128 + 1) + 4 bytes per ray; one stream per handle at a time). */
 int ffn_render_samples(ffn_net_t* net, const float* positions, const float* view_directions,
                        const float* t_values, int64_t num_rays, int32_t num_samples,
                        float* color, float* alpha, float* depth, int32_t* nan_flag, void* stream);

@@ -383,6 +383,8 @@ def test_render_stream_pipeline_on_the_gpu(golden_nerf):
     valid = torch.nonzero(s.valid_mask).flatten()
     batches = [valid[i * 1000:(i + 1) * 1000 + 37 * i] for i in range(5)]
     rc = ffn.Raycaster(m)
+    with torch.no_grad():
+        rc.render(s.sample(batches[0], None).to(DEV), True)      # (packs the weight image)
     before = _lib.launch_count()
     got = list(rc.render_stream(s, batches, True))
     assert _lib.launch_count() - before == len(batches)
@@ -391,3 +393,44 @@ def test_render_stream_pipeline_on_the_gpu(golden_nerf):
             want = rc.render(s.sample(b, None).to(DEV), True).numpy()
             np.testing.assert_array_equal(r.color, want.color)
             np.testing.assert_array_equal(r.depth, want.depth)
+
+
+def test_fp16x3_precise_mode_matches_fp32(golden_nerf):
+    """operand="fp16x3": hi + residual split of every tensor-core operand (three UMMAs per product).  On the sharpened
+    golden net (sigma up to 50, colour logits x6) the fast fp16 mode is within 2.5e-3 of the reference's pixels; the
+    precise mode must be within 5e-5 (fp32 SGEMM reassociation level), raw outputs within 2e-5 relative, depth equal."""
+    g, m = golden_nerf
+    import copy
+    mp = copy.deepcopy(m)
+    mp.ffn_operand = "fp16x3"
+    s = ffn.RaySamples(*[cuda(g[k]) for k in ("positions", "view_directions", "t_values")], None)
+    with torch.no_grad():
+        before = _lib.launch_count()
+        out = ffn.Raycaster(mp).render(s, True)
+        raw = mp(cuda(g["positions"]).reshape(-1, 3), cuda(g["view_directions"]).reshape(-1, 3))
+        fast = ffn.Raycaster(m).render(s, True)
+    assert _lib.launch_count() > before
+    err = np.abs(out.color.cpu().numpy() - g["color"]).max()
+    err_a = np.abs(out.alpha.cpu().numpy() - g["alpha"]).max()
+    err_fast = np.abs(fast.color.cpu().numpy() - g["color"]).max()
+    print("fp16x3 colour %.2e alpha %.2e (fast mode %.2e)" % (err, err_a, err_fast))
+    assert err <= 5e-5 and err_a <= 5e-5, (err, err_a)
+    assert err < 0.2 * err_fast
+    assert np.abs(raw.cpu().numpy() - g["raw"]).max() <= 2e-5 * np.abs(g["raw"]).max()
+    assert (out.depth.cpu().numpy() != g["depth"]).mean() == 0
+    # rays mode, a size with several tiles per cluster, samples-per-ray that straddles tiles
+    R, S = 3000, 192
+    rng = np.random.default_rng(5)
+    o = np.tile(np.array([[0.1, 0.2, -4.0]], np.float32), (R, 1))
+    d = rng.normal(size=(R, 3)).astype(np.float32) * 0.12 + np.array([0, 0, 1], np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    near, far = rng.uniform(2.8, 3.3, R).astype(np.float32), rng.uniform(4.5, 5.2, R).astype(np.float32)
+    u = rng.random((R, S), dtype=np.float32)
+    ref_s = oracle.sample_rays(o, d, near, far, S, u=u)
+    ref = oracle.render_rays(lambda p, v: oracle.nerf_forward(weights(g), p, v), ref_s, True)
+    eng = engine.get_engine(mp, torch.device(DEV))
+    c, a, dep, _ = eng.net.render_rays(cuda(o), cuda(d), cuda(near), cuda(far), torch.linspace(0, 1, S).to(DEV), cuda(u),
+                                       True, 0, 0, S, True)
+    assert np.abs(c.cpu().numpy() - ref.color).max() <= 5e-5
+    assert np.abs(a.cpu().numpy() - ref.alpha).max() <= 5e-5
+    assert (dep.cpu().numpy() != ref.depth).mean() <= 1e-3
