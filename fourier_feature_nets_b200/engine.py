@@ -142,11 +142,29 @@ def mark_weights_changed():
     _OPT_GENERATION[0] += 1
 
 
+def default_operand(model) -> str:
+    """``model.ffn_operand`` if set, else the ``FFN_OPERAND`` environment variable (lets the reference's unchanged
+    scripts select a mode), else fp16.  "fp16x3" = the precise inference mode (NeRF handles)."""
+    return getattr(model, "ffn_operand", None) or os.environ.get("FFN_OPERAND") or DEFAULT_OPERAND
+
+
+def coarse_operand(model) -> str:
+    """Operand mode of the coarse opacity pass of hierarchical sampling (``model.ffn_coarse_operand`` /
+    ``FFN_COARSE_OPERAND``; default: the model's own mode).  Inverse-transform sampling amplifies differences of the
+    coarse opacities (ray_sampler.py:325-355), so "fp16x3" here makes the sample positions -- and with them the frames --
+    follow the reference's fp32 path closely at ~1.8x the frame time."""
+    return getattr(model, "ffn_coarse_operand", None) or os.environ.get("FFN_COARSE_OPERAND") or default_operand(model)
+
+
 def get_engine(model, device: torch.device, operand: Optional[str] = None) -> Engine:
-    operand = operand or getattr(model, "ffn_operand", DEFAULT_OPERAND)
-    eng = model.__dict__.get("_ffn_engine")
-    if eng is None or eng.device != device or eng.operand != operand or eng.enc_sig != _encoding_signature(model):
-        eng = Engine(model, device, operand)
-        model.__dict__["_ffn_engine"] = eng
+    """The engine (C handle + packed weights) of ``model`` for one operand mode; one per mode is kept."""
+    operand = operand or default_operand(model)
+    if operand == "fp16x3" and getattr(model, "_ffn_kind", None) != "nerf":
+        operand = DEFAULT_OPERAND          # the precise mode covers NeRF handles
+    engines = model.__dict__.setdefault("_ffn_engines", {})
+    eng = engines.get(operand)
+    if eng is None or eng.device != device or eng.enc_sig != _encoding_signature(model):
+        eng = engines[operand] = Engine(model, device, operand)
+    model.__dict__["_ffn_engine"] = eng      # the most recently used one (NaN flag checks, trainers)
     eng.sync_weights(model)
     return eng

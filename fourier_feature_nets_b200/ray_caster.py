@@ -92,8 +92,7 @@ class Raycaster(nn.Module):
             if v:
                 flag.zero_()
             assert not (v & 1), "NaN in rendered colour/opacity"
-        eng = self.model.__dict__.get("_ffn_engine")
-        if eng is not None:
+        for eng in list(self.model.__dict__.get("_ffn_engines", {}).values()):
             flag = eng.net.nan_flag()
             assert not (flag & 0x40000000), "libffn_b200: shared memory base is not 1024-byte aligned"
             assert not (flag & 1), "NaN in rendered colour/opacity"

@@ -169,7 +169,7 @@ class FocusBundle(RayBundle):
         lin_c, lin_u = torch.linspace(0, 1, n_f).to(dev), torch.linspace(0, 1, n_u).to(dev)
         model = self.coarse_model
         if _engine.supported(model) and getattr(model, "use_view", False):
-            eng = _engine.get_engine(model, dev)
+            eng = _engine.get_engine(model, dev, _engine.coarse_operand(model))
             return eng.net.focus_sample(self.starts, self.directions, self.near_raw, self.far_raw, self.near,
                                         self.far, lin_c, lin_u, self.jitter, self.u_focus, self.stratified,
                                         self.seed, S, self.ray_offset)

@@ -39,7 +39,8 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_library_has_blackwell_sass():
     """tcgen05 / TMEM / bulk-copy instructions are in the cubin (B200_PROFILING.md table)."""
     out = subprocess.run(["cuobjdump", "-sass", _lib.build()], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP"):
+    # tcgen05.mma (cta_group::2 in the render kernels), tcgen05.ld, 2-SM tensor-map loads of the weight ring, TMA stores
+    for mnemonic in ("UTCHMMA.2CTA", "LDTM", "UTMALDG.2D.2CTA", "UTMASTG", "UTCBAR.2CTA.MULTICAST"):
         assert mnemonic in out, mnemonic
     assert "HMMA." not in out.replace("UTCHMMA", "")   # no legacy mma.sync path
 

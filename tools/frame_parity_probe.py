@@ -22,9 +22,11 @@ def main():
     ap.add_argument("--res", type=int, default=40)
     ap.add_argument("--samples", type=int, default=32)
     ap.add_argument("--frames", type=int, default=3)
+    ap.add_argument("--operand", default="fp16", choices=["fp16", "bf16", "fp16x3"])
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     model = ffn.load_model(args.model).to(dev).eval()
+    model.ffn_operand = args.operand
     cams = ffn.orbit(np.array([0, 1, 0], np.float32), np.array([0, 0, -1], np.float32), args.frames, 40,
                      ffn.Resolution(args.res, args.res), 4)
     bounds = np.diag([2, 2, 2, 1]).astype(np.float32)

@@ -52,8 +52,10 @@ def fit_arm(pkg, data, args, dev, label):
     return model, out
 
 
-def inference_parity(model, ref_pkg, ref_model, val, dev):
+def inference_parity(model, ref_pkg, ref_model, val, dev, operand="fp16"):
     """Our fused kernel vs the fp32 PyTorch definition (and the reference's own render) on every validation camera."""
+    model = copy.deepcopy(model)
+    model.ffn_operand = operand
     rc = ffn.Raycaster(model.eval())
     worst_c = worst_a = 0.0
     mse, n, mism, rays_n, worst_ref = 0.0, 0, 0, 0, 0.0
@@ -165,6 +167,7 @@ def main():
     val = ffn.ImageDataset.load(data, "val", args.samples, True, False).to(dev)
     train = ffn.ImageDataset.load(data, "train", args.samples, True, True).to(dev)
     res["inference_parity_converged_model"] = inference_parity(ours_model, None, None, val, dev)
+    res["inference_parity_converged_model_fp16x3"] = inference_parity(ours_model, None, None, val, dev, "fp16x3")
     if ref_model is not None:
         # the reference-trained weights in our model: the other direction of the drop-in
         m2 = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True).to(dev)
@@ -178,6 +181,7 @@ def main():
         stress.opacity_out.weight.mul_(k)
         stress.opacity_out.bias.mul_(k)
     res["inference_parity_sigma350_stress"] = dict(inference_parity(stress, None, None, val, dev), opacity_scale=round(k, 2))
+    res["inference_parity_sigma350_stress_fp16x3"] = inference_parity(stress, None, None, val, dev, "fp16x3")
     res["gradients_vs_fp64"] = gradient_check(ours_model, train, dev)
     print(json.dumps(res))
     if args.out:
