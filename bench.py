@@ -392,7 +392,7 @@ def main():
                          # ncu (one --set full capture): dram bytes of a launch of `rays_per_launch` rays, scaled
                          "traffic": None if traffic is None else
                          traffic["dram_bytes_per_launch"] * R / traffic.get("rays_per_launch", R),
-                         "kernel": "ffn_render_kernel<%s,INFER,pair>" % args.operand, "kernel_ms": kernel_ms,
+                         "kernel": "ffn_infer_kernel<%s>" % args.operand, "kernel_ms": kernel_ms,
                          "flop_per_launch": R * SAMPLES * FLOP_PER_SAMPLE,
                          "hbm_gbs_algorithmic": R * 52 / (kernel_ms / 1e3) / 1e9},
             "e2e": {"value": world * R * K / (e2e_ms / 1e3), "unit": "rays/s", "h2d_bytes_per_step": R * 40,

@@ -576,8 +576,8 @@ extern "C" int ffn_net_pack(ffn_net_t* net, const float* const* weights, const f
   dim3 grid(40, net->num_layers);
   if (net->bf16) pack_weights_kernel<true><<<grid, 256, 0, stream>>>(pa, net->d_colmap, net->d_wpack);
   else pack_weights_kernel<false><<<grid, 256, 0, stream>>>(pa, net->d_colmap, net->d_wpack);
-  if (net->bf16) pack_const_kernel<true><<<1, 256, 0, stream>>>(pa, net->d_cparams, net->d_wpack);
-  else pack_const_kernel<false><<<1, 256, 0, stream>>>(pa, net->d_cparams, net->d_wpack);
+  if (net->bf16) pack_const_kernel<true><<<16, 256, 0, stream>>>(pa, net->d_cparams, net->d_wpack);
+  else pack_const_kernel<false><<<16, 256, 0, stream>>>(pa, net->d_cparams, net->d_wpack);
   g_launches += 2;
   if (net->precise) {
     pack_weights_kernel<false, true><<<grid, 256, 0, stream>>>(pa, net->d_colmap, net->d_wpack + net->wpack_bytes);

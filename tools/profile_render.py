@@ -16,7 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--rays", type=int, default=262144)
 ap.add_argument("--samples", type=int, default=64)
 ap.add_argument("--iters", type=int, default=4)
-ap.add_argument("--operand", default="fp16")
+ap.add_argument("--operand", default="fp16", choices=["fp16", "bf16", "fp16x3"])
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.manual_seed(20080524)
