@@ -88,6 +88,19 @@ struct ffn_net {
   size_t ray_scratch_bytes = 0;
   long long gen = 0;            // bumped by every pack
   bool packed = false;
+  // inference-only FOLDED program (NeRF): bottleneck has no activation (nerf_model.py:119-122), so
+  //   hidden_view([bottleneck(h) | enc_v]) = (W_hv[:, :256] W_b) h + W_hv[:, 256:] enc_v + (W_hv[:, :256] b_b + b_hv)
+  // is ONE 256+64 -> 128 layer: one 256x256 UMMA layer and one epilogue per tile less (-11 % tensor work).  Being 128
+  // wide it leaves columns [128,256) of the last trunk layer's accumulator intact, so half of opacity_out's fp32 dot
+  // product moves behind the hand-over of that layer's A operand (LayerDesc::sigma_head = 2).
+  LayerDesc layers_inf[kMaxMmaLayers];
+  int num_layers_inf = 0;
+  uint32_t fold_w_off = 0, fold_bias_off = 0;
+  int fold_colmap_off = 0;      // view-encoding column map (64 entries) of the folded layer's fifth K-chunk
+  int fold_hv_in = 0;           // in_features of hidden_view
+  long long fold_gen = -1;      // pack generation the folded image was built from (built lazily by the first render)
+  const float* last_w[FFN_MAX_LAYERS + 4] = {nullptr};
+  const float* last_b[FFN_MAX_LAYERS + 4] = {nullptr};
   // training (NeRF handles): backward program + slot bookkeeping
   bool trainable = false;
   LayerDesc layers_bwd[kMaxMmaLayers];
@@ -189,6 +202,42 @@ __global__ void pack_const_kernel(const __grid_constant__ PackArgs pa, ConstPara
         cp->head_w[pa.head_first[h] + o][i] = i < inf ? w[(size_t)o * inf + i] : 0.f;
       if (tid == 0) cp->head_b[pa.head_first[h] + o] = b[o];
     }
+  }
+}
+
+// The folded layer of the inference program (ffn_net::layers_inf): row n = W_hv[n, :256] W_b | W_hv[n, 256:]
+// (fp32, ascending summation order, then ONE rounding to the operand dtype); bias tile W_hv[:, :256] b_b + b_hv.
+// One thread per (row, K column); 16-bit scattered stores.
+template <bool kBF16>
+__global__ void pack_fold_kernel(const float* __restrict__ w_b, const float* __restrict__ b_b,
+                                 const float* __restrict__ w_hv, const float* __restrict__ b_hv,
+                                 int hv_in,
+                                 const int* __restrict__ view_colmap, uint8_t* __restrict__ wpack, uint32_t w_off,
+                                 uint32_t bias_off) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = idx / 320, k = idx - n * 320;
+  if (n >= kFoldedN) return;
+  auto round16 = [](float v) -> float {
+    if constexpr (kBF16) return __bfloat162float(__float2bfloat16_rn(v));
+    else return __half2float(__float2half_rn(v));
+  };
+  float v = 0.f;
+  if (k < 256) {
+    for (int m = 0; m < 256; ++m) v = fmaf(w_hv[(size_t)n * hv_in + m], w_b[(size_t)m * 256 + k], v);
+  } else {
+    const int col = view_colmap[k - 256];
+    v = col >= 0 ? w_hv[(size_t)n * hv_in + col] : 0.f;
+  }
+  const int ch = k >> 6, kk = k & 63, u = kk >> 3, e = kk & 7;
+  const size_t off = (size_t)w_off + (size_t)ch * kFoldedN * 128 + (size_t)n * 128 + (size_t)((u ^ (n & 7)) << 4) + e * 2;
+  *reinterpret_cast<uint16_t*>(wpack + off) = (uint16_t)(ptx::pack2<kBF16, false>(v, 0.f) & 0xffffu);
+  if (k == 0) {
+    float b = 0.f;
+    for (int m = 0; m < 256; ++m) b = fmaf(w_hv[(size_t)n * hv_in + m], b_b[m], b);
+    b += b_hv[n];
+    const float hi = round16(b);
+    *reinterpret_cast<uint32_t*>(wpack + bias_off + (size_t)(n >> 3) * kBiasTileSBO + (size_t)(n & 7) * 16) =
+        ptx::pack2<kBF16, false>(hi, b - hi);
   }
 }
 
@@ -327,6 +376,10 @@ static int finalize_net(ffn_net* net) {
     net->layers[l].bias_off = net->pack_layers[l].bias_off = off;
     if (has_bias) off += (uint32_t)net->layers[l].n * 32u;
   }
+  if (net->kind == ENC_NERF) {      // the folded inference layer: 5 K-chunks of kFoldedN rows + its bias tile
+    net->fold_w_off = off; off += (uint32_t)kFoldedN * 128u * 5u;
+    net->fold_bias_off = off; off += (uint32_t)kFoldedN * 32u;
+  }
   net->wpack_bytes = off;
   CUDA_TRY(cudaMalloc(&net->d_wpack, net->wpack_bytes * (net->precise ? 2 : 1)));
   CUDA_TRY(cudaMemset(net->d_wpack, 0, net->wpack_bytes * (net->precise ? 2 : 1)));
@@ -432,6 +485,18 @@ extern "C" int ffn_nerf_create(const ffn_nerf_desc_t* d, ffn_net_t** out) {
   net->heads.push_back(PackHead{L, 256, 3, 1});        // opacity_out -> out[3]
   net->heads.push_back(PackHead{L + 3, 128, 0, 3});    // color_out   -> out[0..2]
   if (finalize_net(net) || build_nerf_backward(net, L)) { ffn_net_destroy(net); return 1; }
+  {  // folded inference program: the trunk as above (no CUDA-core sigma head), then one 144-wide layer
+    memcpy(net->layers_inf, net->layers, sizeof(net->layers));
+    net->layers_inf[L - 1].sigma_head = 2;
+    LayerDesc& ld = net->layers_inf[L];
+    ld = net->layers[L + 1];                       // hidden_view: sources (chunks 0-3 + view encoding), ReLU, rgb heads
+    ld.n = kFoldedN; ld.has_bias = 1;
+    ld.w_offset = net->fold_w_off; ld.bias_off = net->fold_bias_off;
+    memset(&net->layers_inf[L + 1], 0, sizeof(LayerDesc));
+    net->num_layers_inf = L + 1;
+    net->fold_colmap_off = net->pack_layers[L + 1].colmap_off + 4 * 64;
+    net->fold_hv_in = 256 + n_view;
+  }
   ConstParams* h = new ConstParams();
   memset(h, 0, sizeof(ConstParams));
   for (int k = 0; k < Fp; ++k) h->freq_pos[k] = d->freq_pos[k];
@@ -560,6 +625,7 @@ extern "C" int ffn_net_pack(ffn_net_t* net, const float* const* weights, const f
   for (int i = 0; i < net->num_linear; ++i) {
     if (!weights[i] || !biases[i]) return fail("ffn_net_pack: null weight/bias pointer");
     pa.w[i] = weights[i]; pa.b[i] = biases[i];
+    net->last_w[i] = weights[i]; net->last_b[i] = biases[i];
   }
   pa.n_layers = net->num_layers;
   for (int l = 0; l < net->num_layers; ++l) {
@@ -631,8 +697,30 @@ static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int 
   } else {
     ka.wpack = net->d_wpack; arena_bytes = net->wpack_bytes * (net->precise ? 2 : 1);
     ka.wpack_lo_off = (uint32_t)net->wpack_bytes;
-    memcpy(ka.layers, net->layers, sizeof(net->layers));
-    ka.num_layers = net->num_layers;
+    static const bool env_nofold = getenv("FFN_FOLD") != nullptr && atoi(getenv("FFN_FOLD")) == 0;
+    const bool folded = pass == PASS_INFER && !net->precise && ka.dbg_layer < 0 && net->num_layers_inf > 0 && !env_nofold;
+    if (folded) {
+      if (net->fold_gen != net->gen) {      // weights changed since the folded image was built
+        const int L = net->num_linear - 4;
+        const int threads = 256, blocks = (kFoldedN * 320 + threads - 1) / threads;
+        if (net->bf16)
+          pack_fold_kernel<true><<<blocks, threads, 0, stream>>>(net->last_w[L + 1], net->last_b[L + 1], net->last_w[L + 2],
+              net->last_b[L + 2], net->fold_hv_in, net->d_colmap + net->fold_colmap_off, net->d_wpack, net->fold_w_off,
+              net->fold_bias_off);
+        else
+          pack_fold_kernel<false><<<blocks, threads, 0, stream>>>(net->last_w[L + 1], net->last_b[L + 1], net->last_w[L + 2],
+              net->last_b[L + 2], net->fold_hv_in, net->d_colmap + net->fold_colmap_off, net->d_wpack, net->fold_w_off,
+              net->fold_bias_off);
+        CUDA_TRY(cudaGetLastError());
+        g_launches += 1;
+        net->fold_gen = net->gen;
+      }
+      memcpy(ka.layers, net->layers_inf, sizeof(net->layers_inf));
+      ka.num_layers = net->num_layers_inf;
+    } else {
+      memcpy(ka.layers, net->layers, sizeof(net->layers));
+      ka.num_layers = net->num_layers;
+    }
   }
   for (int i = 0; i < 4; ++i)
     if (ffn_encode_rows128(&ka.wmap[i], ka.wpack, arena_bytes, 16 << i) != 0)

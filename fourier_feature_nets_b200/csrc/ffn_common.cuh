@@ -28,6 +28,11 @@ constexpr int kSmemMiscBytes = 3072;
 constexpr int kSmemTotal = kSmemMisc + kSmemMiscBytes;          // 232448 = 227 KiB (the sm_100 maximum)
 
 constexpr int kMaxMmaLayers = 12;
+constexpr int kFoldedN = 128;                  // folded bottleneck . hidden_view layer of the inference program
+// index of the weight-arena tensor map whose box is `rows` rows of 128 bytes (16 / 32 / 64 / 128)
+__host__ __device__ __forceinline__ int wmap_index(uint32_t rows) {
+  return rows >= 128 ? 3 : rows >= 64 ? 2 : rows >= 32 ? 1 : 0;
+}
 constexpr int kMaxChunksPerLayer = 6;
 // warps 0-3: weight producer / UMMA issuer / TMEM alloc / ones tile; 4-7, 8-11: epilogue warpgroup of slot 0 / 1.
 // (A helper warpgroup per slot, lock-step weight sharing between the slots, single-CTA UMMAs and an A-operand-in-TMEM
@@ -53,7 +58,10 @@ struct LayerDesc {
   uint8_t n_chunks;
   uint8_t epi;                             // EPI_*
   uint8_t accumulate;                      // 1: first MMA accumulates onto the existing TMEM tile
-  uint8_t sigma_head;                      // 1: also emit out[3] = head_w[3] . h + head_b[3] from this layer's fp32 h
+  uint8_t sigma_head;                      // 1: also emit out[3] = head_w[3] . h + head_b[3] from this layer's fp32 h;
+                                           // 2 (folded inference program): columns [128,256) of that dot product are
+                                           // read from TMEM AFTER the A operand has been handed over (the next layer is
+                                           // 128 wide and leaves those accumulator columns intact)
   uint8_t write_view_enc;                  // 1: after this layer, overwrite the enc chunk with the view encoding
   uint8_t bias_row;                        // row of ConstParams::bias
   uint8_t src[kMaxChunksPerLayer];         // A chunk index (0..3 act, 4 enc) per K-chunk

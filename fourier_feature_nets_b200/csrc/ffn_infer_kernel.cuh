@@ -97,6 +97,146 @@ __device__ __forceinline__ void store_enc_regs(const uint32_t (&pk)[32], uint32_
     ptx::st_shared_v4(row_addr + ((u ^ row7) << 4), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
 }
 
+// One layer epilogue of the inference kernel as a STREAM of 32-column accumulator blocks: three register buffers in
+// rotation, the tcgen05.ld of blocks b+1 / b+2 in flight while block b is converted and stored.  (LDTM completion is
+// tracked by scoreboard, so a consumer only waits for its own block; the tcgen05.wait::ld points keep the PTX legal:
+// every register is read after a wait that follows its load.)  lean_layer_epilogue's one-x64-load-at-a-time drain
+// serialises load latency and conversion (4 x ~440 cycles per 256-wide layer); here the TMEM read port stays busy.
+//   kSigmaBlocks > 0: additionally the fp32 dot product of the activated columns [0, 32 kSigmaBlocks) of the row with
+//           head 3 (opacity_out, nerf_model.py:117) as four partial sums hsum[0..3] (column j -> sum j & 3)
+template <bool kBF16, bool kRelu, int kSigmaBlocks, int kNblk>
+__device__ __forceinline__ void stream_layer_epilogue(uint32_t taddr_base, uint32_t act_row, uint32_t row7,
+                                                      float* hsum = nullptr) {
+  static_assert(kNblk == 8 || kNblk == 4, "256- or 128-wide layers");
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if constexpr (kSigmaBlocks > 0) { a0 = hsum[0]; a1 = hsum[1]; a2 = hsum[2]; a3 = hsum[3]; }
+  auto conv = [&](uint32_t (&v)[32], auto bc) {
+    constexpr int b = decltype(bc)::value;
+    if constexpr (b < kSigmaBlocks) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        a0 = fmaf(kRelu ? fmaxf(__uint_as_float(v[j + 0]), 0.f) : __uint_as_float(v[j + 0]), c_params.head_w[3][b * 32 + j + 0], a0);
+        a1 = fmaf(kRelu ? fmaxf(__uint_as_float(v[j + 1]), 0.f) : __uint_as_float(v[j + 1]), c_params.head_w[3][b * 32 + j + 1], a1);
+        a2 = fmaf(kRelu ? fmaxf(__uint_as_float(v[j + 2]), 0.f) : __uint_as_float(v[j + 2]), c_params.head_w[3][b * 32 + j + 2], a2);
+        a3 = fmaf(kRelu ? fmaxf(__uint_as_float(v[j + 3]), 0.f) : __uint_as_float(v[j + 3]), c_params.head_w[3][b * 32 + j + 3], a3);
+      }
+    }
+    store_act_block<kBF16, kRelu>(v, act_row + (uint32_t)(b >> 1) * kChunkBytesA, row7, (uint32_t)(b & 1) * 4u);
+  };
+  auto blk = [&](auto bc) { return taddr_base + (uint32_t)decltype(bc)::value * 32u; };
+  using std::integral_constant;
+  uint32_t A[32], B[32], C[32];
+  ptx::tmem_ld32(blk(integral_constant<int, 0>{}), A);
+  ptx::tmem_ld32(blk(integral_constant<int, 1>{}), B);
+  ptx::tmem_wait_ld2(A, B);
+  ptx::tmem_ld32(blk(integral_constant<int, 2>{}), C);
+  conv(A, integral_constant<int, 0>{});
+  ptx::tmem_ld32(blk(integral_constant<int, 3>{}), A);
+  conv(B, integral_constant<int, 1>{});
+  ptx::tmem_wait_ld2(C, A);
+  if constexpr (kNblk == 8) {
+    ptx::tmem_ld32(blk(integral_constant<int, 4>{}), B);
+    conv(C, integral_constant<int, 2>{});
+    ptx::tmem_ld32(blk(integral_constant<int, 5>{}), C);
+    conv(A, integral_constant<int, 3>{});
+    ptx::tmem_wait_ld2(B, C);
+    ptx::tmem_ld32(blk(integral_constant<int, 6>{}), A);
+    conv(B, integral_constant<int, 4>{});
+    ptx::tmem_ld32(blk(integral_constant<int, 7>{}), B);
+    conv(C, integral_constant<int, 5>{});
+    ptx::tmem_wait_ld2(A, B);
+    conv(A, integral_constant<int, 6>{});
+    conv(B, integral_constant<int, 7>{});
+  } else {
+    conv(C, integral_constant<int, 2>{});
+    conv(A, integral_constant<int, 3>{});
+  }
+  if constexpr (kSigmaBlocks > 0) { hsum[0] = a0; hsum[1] = a1; hsum[2] = a2; hsum[3] = a3; }
+}
+
+// The other half of opacity_out's dot product (LayerDesc::sigma_head == 2): columns [128, 256) of the last trunk
+// layer's accumulator, read again AFTER the layer's A operand has been handed over -- the folded layer that follows is
+// 128 wide and leaves them intact -- i.e. while this warpgroup would otherwise wait for the tensor core.
+__device__ __forceinline__ void sigma_tail(uint32_t taddr_base, float (&hs)[4]) {
+  float a0 = hs[0], a1 = hs[1], a2 = hs[2], a3 = hs[3];
+  auto dot = [&](const uint32_t (&v)[32], auto bc) {
+    constexpr int b = decltype(bc)::value;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      a0 = fmaf(fmaxf(__uint_as_float(v[j + 0]), 0.f), c_params.head_w[3][b * 32 + j + 0], a0);
+      a1 = fmaf(fmaxf(__uint_as_float(v[j + 1]), 0.f), c_params.head_w[3][b * 32 + j + 1], a1);
+      a2 = fmaf(fmaxf(__uint_as_float(v[j + 2]), 0.f), c_params.head_w[3][b * 32 + j + 2], a2);
+      a3 = fmaf(fmaxf(__uint_as_float(v[j + 3]), 0.f), c_params.head_w[3][b * 32 + j + 3], a3);
+    }
+  };
+  using std::integral_constant;
+  uint32_t A[32], B[32];
+  ptx::tmem_ld32(taddr_base + 4u * 32u, A);
+  ptx::tmem_ld32(taddr_base + 5u * 32u, B);
+  ptx::tmem_wait_ld2(A, B);
+  dot(A, integral_constant<int, 4>{});
+  ptx::tmem_ld32(taddr_base + 6u * 32u, A);
+  dot(B, integral_constant<int, 5>{});
+  ptx::tmem_ld32(taddr_base + 7u * 32u, B);
+  ptx::tmem_wait_ld2(A, B);
+  dot(A, integral_constant<int, 6>{});
+  dot(B, integral_constant<int, 7>{});
+  hs[0] = a0; hs[1] = a1; hs[2] = a2; hs[3] = a3;
+}
+
+// The 64-wide view-direction encoding row (nerf_model.py:104-109) of every row of a warp, WITHOUT one sin/cos pair
+// per row and frequency: in the ray modes with S >= 32 the warp's 32 consecutive rows belong to at most two rays, so
+// lane r*16 + p evaluates pair p = 3k + j of ray (first ray + r) once (view_enc_prepare: under the wait for the layer's
+// accumulator, four live registers) and every row collects its 3 f_view pairs by shuffles after the drain
+// (view_enc_finish; bit-identical to posenc_regs: same fp32 product, same reduction, same MUFU).  Needs 3 f_view <= 16.
+struct ViewEncPart {
+  uint32_t mine;       // this lane's (cos, sin) pair
+  int src_base;        // 0 | 16: which half of the warp holds this row's ray
+  float dx, dy, dz;    // this row's view direction (the un-encoded inputs)
+};
+
+template <bool kBF16>
+__device__ __forceinline__ void view_enc_prepare(const KernelArgs& a, ViewEncPart& ve, long long row_g0, long long row_g,
+                                                 int lane) {
+  const long long ray_lo = row_g0 / a.S;
+  const long long off = row_g - ray_lo * a.S;                  // < 2 S: the warp's rows span at most two rays
+  const long long ray = ray_lo + (off >= a.S ? 1 : 0);
+  const long long num_rays = a.M / a.S;
+  const int npairs = 3 * a.f_view;
+  ve.mine = 0u;
+  {
+    const int r = lane >> 4, p = lane & 15;
+    const long long src_ray = ray_lo + r;
+    if (p < npairs && src_ray < num_rays) {
+      const int k = p / 3, j = p - 3 * k;
+      float s, c;
+      sincos_rr(__fmul_rn(__ldg(a.dir + src_ray * 3 + j), c_params.freq_view[k]), s, c);
+      ve.mine = ptx::pack2<kBF16, false>(c, s);
+    }
+  }
+  ve.src_base = ray > ray_lo ? 16 : 0;
+  ve.dx = ve.dy = ve.dz = 0.f;
+  if (row_g < a.M) { ve.dx = __ldg(a.dir + ray * 3 + 0); ve.dy = __ldg(a.dir + ray * 3 + 1); ve.dz = __ldg(a.dir + ray * 3 + 2); }
+  // pin the loads and the sin/cos HERE (before the caller's barrier wait, which is volatile asm as well): left alone the
+  // compiler sinks them to their first use after the drain, i.e. onto the hand-over chain
+  asm volatile("" : "+r"(ve.mine), "+r"(ve.src_base), "+f"(ve.dx), "+f"(ve.dy), "+f"(ve.dz));
+}
+
+template <bool kBF16>
+__device__ __forceinline__ void view_enc_finish(const KernelArgs& a, const ViewEncPart& ve, uint32_t (&pk)[32]) {
+  const int npairs = 3 * a.f_view;
+#pragma unroll
+  for (int p = 0; p < 30; ++p) {
+    pk[p] = 0u;
+    if (p < 16) {
+      const uint32_t got = __shfl_sync(0xffffffffu, ve.mine, ve.src_base + p);
+      if (p < npairs) pk[p] = got;
+    }
+  }
+  pk[30] = a.include_inputs ? ptx::pack2<kBF16, false>(ve.dx, ve.dy) : 0u;
+  pk[31] = a.include_inputs ? ptx::pack2<kBF16, false>(ve.dz, 0.f) : 0u;
+}
+
 // Output heads (color_out / the final Linear: nerf_model.py:123, fourier_feature_models.py:77) from the 16-bit copy
 // of relu(h) this thread has just written to its own row of the slot's activation chunks: kHn fp32 dot products over
 // `ncols` columns, columns in ascending order per head, head weights as constant-bank FFMA operands.  Runs AFTER the
@@ -535,18 +675,20 @@ ffn_infer_kernel(const __grid_constant__ KernelArgs args) {
         arrive_a_ready();
       }
       float out[4] = {0.f, 0.f, 0.f, 0.f};  // raw rgb | sigma of this sample
+      float hs[4] = {0.f, 0.f, 0.f, 0.f};   // partial sums of opacity_out's dot product
+      bool sig_tail = false;
 
       for (int l = 0; l < L; ++l) {
         const LayerDesc& ld = args.layers[l];
         const int nblk_all = ld.n >> 5;                 // 32-column blocks of this layer (8 or 4)
-        uint32_t vpk[32];
+        ViewEncPart ve;
+        ve.mine = 0u; ve.src_base = 0; ve.dx = ve.dy = ve.dz = 0.f;
+        const bool ve_dedup = ld.write_view_enc && args.mode != MODE_SAMPLES && args.S >= 32 && 3 * args.f_view <= 16;
         if (ld.write_view_enc) {
-          // the view encoding that replaces the position encoding after this layer: computed while the tensor core
-          // still works on the layer (the warpgroup would otherwise idle), stored once its accumulator is complete
-          float dx, dy, dz;
-          dx = dy = dz = 0.f;
-          if (valid) row_view(args, row_g, dx, dy, dz);
-          posenc_regs<kBF16>(vpk, dx, dy, dz, c_params.freq_view, args.f_view, args.include_inputs != 0);
+          // the view encoding that replaces the position encoding after this layer: loads and sin/cos while the tensor
+          // core still works on the layer (the warpgroup would otherwise idle), stored once its accumulator is complete
+          if (ve_dedup) view_enc_prepare<kBF16>(args, ve, tile * kTileM + wq * 32, row_g, lane);     // (warp-uniform)
+          else if (valid) row_view(args, row_g, ve.dx, ve.dy, ve.dz);
         }
         ptx::mbar_wait(my_acc_full, acc_phase);
         acc_phase ^= 1u;
@@ -566,8 +708,10 @@ ffn_infer_kernel(const __grid_constant__ KernelArgs args) {
             // last layer: relu(h) goes to this thread's own row of the activation chunks like any other layer, the
             // accumulator is handed back ("drained": the next tile's first UMMA may overwrite it) and only then the
             // fp32 dot products run, from the 16-bit copy
-            lean_layer_epilogue<kBF16, true, PASS_INFER, false>(taddr_base, 0, nblk_all, slot_base + row_off, row7, nullptr,
-                                                                nullptr, valid);
+            if (nblk_all == 4) stream_layer_epilogue<kBF16, true, 0, 4>(taddr_base, slot_base + row_off, row7);
+            else if (nblk_all == 8) stream_layer_epilogue<kBF16, true, 0, 8>(taddr_base, slot_base + row_off, row7);
+            else lean_layer_epilogue<kBF16, true, PASS_INFER, false>(taddr_base, 0, nblk_all, slot_base + row_off, row7, nullptr,
+                                                                     nullptr, valid);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar_drained + 8 * slot);
@@ -586,18 +730,26 @@ ffn_infer_kernel(const __grid_constant__ KernelArgs args) {
         } else if (ld.sigma_head && ld.epi == EPI_RELU_ACT && args.dbg_layer != l && ld.n == 256) {
           // trunk layer that also feeds opacity_out (nerf_model.py:118): the lean path plus one fp32 dot product with
           // the fp32 accumulator values (four independent partial sums)
-          float hs[4] = {0.f, 0.f, 0.f, 0.f};
-          lean_layer_epilogue<kBF16, true, PASS_INFER, false, true>(taddr_base, 0, 8, slot_base + row_off, row7, nullptr,
-                                                                   nullptr, valid, hs);
-          out[3] = ((hs[0] + hs[1]) + (hs[2] + hs[3])) + c_params.head_b[3];
+          hs[0] = hs[1] = hs[2] = hs[3] = 0.f;
+          if (ld.sigma_head == 2) {
+            stream_layer_epilogue<kBF16, true, 4, 8>(taddr_base, slot_base + row_off, row7, hs);
+            sig_tail = true;        // columns [128, 256): after the hand-over below
+          } else {
+            stream_layer_epilogue<kBF16, true, 8, 8>(taddr_base, slot_base + row_off, row7, hs);
+            out[3] = ((hs[0] + hs[1]) + (hs[2] + hs[3])) + c_params.head_b[3];
+          }
         } else if (ld.epi != EPI_RELU_HEAD && !ld.sigma_head && args.dbg_layer != l) {
           // lean path (the bias is already in the accumulator)
-          if (ld.epi == EPI_RELU_ACT)
+          if (nblk_all == 8) {
+            if (ld.epi == EPI_RELU_ACT) stream_layer_epilogue<kBF16, true, 0, 8>(taddr_base, slot_base + row_off, row7);
+            else stream_layer_epilogue<kBF16, false, 0, 8>(taddr_base, slot_base + row_off, row7);
+          } else if (ld.epi == EPI_RELU_ACT) {
             lean_layer_epilogue<kBF16, true, PASS_INFER, false>(taddr_base, 0, nblk_all, slot_base + row_off, row7, nullptr,
                                                                 nullptr, valid);
-          else
+          } else {
             lean_layer_epilogue<kBF16, false, PASS_INFER, false>(taddr_base, 0, nblk_all, slot_base + row_off, row7, nullptr,
                                                                  nullptr, valid);
+          }
         } else {
           // general path: fp32 values are needed (odd head shapes, debug dump)
           const bool relu = ld.epi != EPI_LINEAR_ACT;
@@ -651,7 +803,13 @@ ffn_infer_kernel(const __grid_constant__ KernelArgs args) {
             if (o < hn) out[o] = hacc[o] + c_params.head_b[o];
         }
 
-        if (ld.write_view_enc) store_enc_regs(vpk, enc_row_addr, row7);
+        if (ld.write_view_enc) {
+          // (the tensor core has finished reading the position encoding: the layer's accumulator is complete)
+          uint32_t vpk[32];
+          if (ve_dedup) view_enc_finish<kBF16>(args, ve, vpk);
+          else posenc_regs<kBF16>(vpk, ve.dx, ve.dy, ve.dz, c_params.freq_view, args.f_view, args.include_inputs != 0);
+          store_enc_regs(vpk, enc_row_addr, row7);
+        }
         if (l < L - 1) arrive_a_ready();
 
         if (eprof) {
@@ -659,6 +817,11 @@ ffn_infer_kernel(const __grid_constant__ KernelArgs args) {
           e_work += n - e_t;
           if (l < 20) atomicAdd(args.stats + 8 + l, (unsigned long long)(n - e_t));
           e_t = n;
+        }
+        if (sig_tail) {      // (off the chain: the tensor core already has this slot's next A operand)
+          sigma_tail(taddr_base, hs);
+          out[3] = ((hs[0] + hs[1]) + (hs[2] + hs[3])) + c_params.head_b[3];
+          sig_tail = false;
         }
       }
       ptx::tc_fence_before();

@@ -181,7 +181,7 @@ ffn_infer_x3_kernel(const __grid_constant__ KernelArgs args) {
                                            : ld.w_offset + (uint32_t)(j >> 1) * bytes + ((j & 1) ? args.wpack_lo_off : 0u);
             const uint32_t hb = nbytes >> 1;
             const uint32_t rows = hb >> 7;
-            const int mi = rows >= 128 ? 3 : rows >= 64 ? 2 : rows >= 32 ? 1 : 0;
+            const int mi = wmap_index(rows);
             if (cta_rank == 0) ptx::mbar_arrive_expect_tx(bar_w_full + 8 * stage, nbytes);
             ptx::tma_load_2d_pair(smem_base + kSmemW + stage * kWStageBytes, &args.wmap[mi], 0,
                                   (int)((src_off + cta_rank * hb) >> 7), full_leader[stage]);

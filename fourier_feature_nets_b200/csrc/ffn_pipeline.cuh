@@ -48,7 +48,7 @@ __device__ __forceinline__ void weight_producer(const KernelArgs& args, const Pi
             // Rows are contiguous in both the SW128 and the bias-tile layout: the arena is a 2-D tensor of 128-byte
             // rows, my half a box of hb / 128 rows.  The leader expects the bytes of BOTH halves on its barrier.
             const uint32_t rows = hb >> 7;
-            const int mi = rows >= 128 ? 3 : rows >= 64 ? 2 : rows >= 32 ? 1 : 0;
+            const int mi = wmap_index(rows);
             if (pc.cta_rank == 0) ptx::mbar_arrive_expect_tx(pc.bar_w_full + 8 * stage, nbytes);
             ptx::tma_load_2d_pair(pc.smem_base + kSmemW + stage * kWStageBytes, &args.wmap[mi], 0,
                                   (int)((src_off + pc.cta_rank * hb) >> 7), full_leader[stage]);
