@@ -46,6 +46,7 @@ struct PackLayer {          // how one MMA layer's weights are gathered from a t
   int colmap_off;           // offset into the colmap array (n_chunks * 64 entries)
   uint32_t w_offset;        // byte offset in the packed arena
   uint32_t bias_off;        // byte offset of the bias tile in the packed arena
+  uint32_t cbias_off;       // ... and of its compact copy (N x 16 B)
   int bias_row;             // >= 0: this MMA layer carries the Linear's bias
 };
 struct PackHead {           // a small output head evaluated on CUDA cores in fp32
@@ -95,7 +96,7 @@ struct ffn_net {
   // product moves behind the hand-over of that layer's A operand (LayerDesc::sigma_head = 2).
   LayerDesc layers_inf[kMaxMmaLayers];
   int num_layers_inf = 0;
-  uint32_t fold_w_off = 0, fold_bias_off = 0;
+  uint32_t fold_w_off = 0, fold_bias_off = 0, fold_cbias_off = 0;
   int fold_colmap_off = 0;      // view-encoding column map (64 entries) of the folded layer's fifth K-chunk
   int fold_hv_in = 0;           // in_features of hidden_view
   long long fold_gen = -1;      // pack generation the folded image was built from (built lazily by the first render)
@@ -133,6 +134,7 @@ struct PackArgs {
   int colmap_off[kMaxMmaLayers];
   uint32_t w_offset[kMaxMmaLayers];
   uint32_t bias_off[kMaxMmaLayers];
+  uint32_t cbias_off[kMaxMmaLayers];
   int bias_row[kMaxMmaLayers];
   int n_heads;
   int head_linear[4], head_in[4], head_first[4], head_n[4];
@@ -191,6 +193,8 @@ __global__ void pack_const_kernel(const __grid_constant__ PackArgs pa, ConstPara
       const uint32_t pk = ptx::pack2<kBF16, false>(hi, v - hi);
       *reinterpret_cast<uint32_t*>(wpack + pa.bias_off[l] + (size_t)(n >> 3) * kBiasTileSBO +
                                    (size_t)(n & 7) * 16) = pk;
+      *reinterpret_cast<uint32_t*>(wpack + pa.cbias_off[l] + (size_t)(n >> 3) * kCBiasTileSBO +
+                                   (size_t)(n & 7) * 16) = pk;
     }
   }
   for (int h = 0; h < pa.n_heads; ++h) {
@@ -213,7 +217,7 @@ __global__ void pack_fold_kernel(const float* __restrict__ w_b, const float* __r
                                  const float* __restrict__ w_hv, const float* __restrict__ b_hv,
                                  int hv_in,
                                  const int* __restrict__ view_colmap, uint8_t* __restrict__ wpack, uint32_t w_off,
-                                 uint32_t bias_off) {
+                                 uint32_t bias_off, uint32_t cbias_off) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = idx / 320, k = idx - n * 320;
   if (n >= kFoldedN) return;
@@ -236,8 +240,9 @@ __global__ void pack_fold_kernel(const float* __restrict__ w_b, const float* __r
     for (int m = 0; m < 256; ++m) b = fmaf(w_hv[(size_t)n * hv_in + m], b_b[m], b);
     b += b_hv[n];
     const float hi = round16(b);
-    *reinterpret_cast<uint32_t*>(wpack + bias_off + (size_t)(n >> 3) * kBiasTileSBO + (size_t)(n & 7) * 16) =
-        ptx::pack2<kBF16, false>(hi, b - hi);
+    const uint32_t pk = ptx::pack2<kBF16, false>(hi, b - hi);
+    *reinterpret_cast<uint32_t*>(wpack + bias_off + (size_t)(n >> 3) * kBiasTileSBO + (size_t)(n & 7) * 16) = pk;
+    *reinterpret_cast<uint32_t*>(wpack + cbias_off + (size_t)(n >> 3) * kCBiasTileSBO + (size_t)(n & 7) * 16) = pk;
   }
 }
 
@@ -376,9 +381,14 @@ static int finalize_net(ffn_net* net) {
     net->layers[l].bias_off = net->pack_layers[l].bias_off = off;
     if (has_bias) off += (uint32_t)net->layers[l].n * 32u;
   }
+  for (int l = 0; l < net->num_layers; ++l) {      // compact bias tiles (N x 16 B), 128-byte aligned rows
+    net->layers[l].cbias_off = net->pack_layers[l].cbias_off = off;
+    if (net->layers[l].has_bias) off += (uint32_t)net->layers[l].n * 16u;
+  }
   if (net->kind == ENC_NERF) {      // the folded inference layer: 5 K-chunks of kFoldedN rows + its bias tile
     net->fold_w_off = off; off += (uint32_t)kFoldedN * 128u * 5u;
     net->fold_bias_off = off; off += (uint32_t)kFoldedN * 32u;
+    net->fold_cbias_off = off; off += (uint32_t)kFoldedN * 16u;
   }
   net->wpack_bytes = off;
   CUDA_TRY(cudaMalloc(&net->d_wpack, net->wpack_bytes * (net->precise ? 2 : 1)));
@@ -491,7 +501,7 @@ extern "C" int ffn_nerf_create(const ffn_nerf_desc_t* d, ffn_net_t** out) {
     LayerDesc& ld = net->layers_inf[L];
     ld = net->layers[L + 1];                       // hidden_view: sources (chunks 0-3 + view encoding), ReLU, rgb heads
     ld.n = kFoldedN; ld.has_bias = 1;
-    ld.w_offset = net->fold_w_off; ld.bias_off = net->fold_bias_off;
+    ld.w_offset = net->fold_w_off; ld.bias_off = net->fold_bias_off; ld.cbias_off = net->fold_cbias_off;
     memset(&net->layers_inf[L + 1], 0, sizeof(LayerDesc));
     net->num_layers_inf = L + 1;
     net->fold_colmap_off = net->pack_layers[L + 1].colmap_off + 4 * 64;
@@ -632,7 +642,7 @@ extern "C" int ffn_net_pack(ffn_net_t* net, const float* const* weights, const f
     const PackLayer& pl = net->pack_layers[l];
     pa.linear[l] = pl.linear; pa.in_features[l] = pl.in_features; pa.n[l] = pl.n;
     pa.n_chunks[l] = pl.n_chunks; pa.colmap_off[l] = pl.colmap_off; pa.w_offset[l] = pl.w_offset;
-    pa.bias_row[l] = pl.bias_row; pa.bias_off[l] = pl.bias_off;
+    pa.bias_row[l] = pl.bias_row; pa.bias_off[l] = pl.bias_off; pa.cbias_off[l] = pl.cbias_off;
   }
   pa.n_heads = (int)net->heads.size();
   for (int h = 0; h < pa.n_heads; ++h) {
@@ -706,11 +716,11 @@ static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int 
         if (net->bf16)
           pack_fold_kernel<true><<<blocks, threads, 0, stream>>>(net->last_w[L + 1], net->last_b[L + 1], net->last_w[L + 2],
               net->last_b[L + 2], net->fold_hv_in, net->d_colmap + net->fold_colmap_off, net->d_wpack, net->fold_w_off,
-              net->fold_bias_off);
+              net->fold_bias_off, net->fold_cbias_off);
         else
           pack_fold_kernel<false><<<blocks, threads, 0, stream>>>(net->last_w[L + 1], net->last_b[L + 1], net->last_w[L + 2],
               net->last_b[L + 2], net->fold_hv_in, net->d_colmap + net->fold_colmap_off, net->d_wpack, net->fold_w_off,
-              net->fold_bias_off);
+              net->fold_bias_off, net->fold_cbias_off);
         CUDA_TRY(cudaGetLastError());
         g_launches += 1;
         net->fold_gen = net->gen;
@@ -722,8 +732,8 @@ static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int 
       ka.num_layers = net->num_layers;
     }
   }
-  for (int i = 0; i < 4; ++i)
-    if (ffn_encode_rows128(&ka.wmap[i], ka.wpack, arena_bytes, 16 << i) != 0)
+  for (int i = 0; i < 5; ++i)
+    if (ffn_encode_rows128(&ka.wmap[i], ka.wpack, arena_bytes, i < 4 ? 16 << i : 8) != 0)
       return fail("cuTensorMapEncodeTiled failed for the weight arena");
   ka.enc_kind = net->kind;
   ka.f_pos = net->f_pos; ka.f_view = net->f_view; ka.include_inputs = net->include_inputs;

@@ -31,7 +31,7 @@ constexpr int kMaxMmaLayers = 12;
 constexpr int kFoldedN = 128;                  // folded bottleneck . hidden_view layer of the inference program
 // index of the weight-arena tensor map whose box is `rows` rows of 128 bytes (16 / 32 / 64 / 128)
 __host__ __device__ __forceinline__ int wmap_index(uint32_t rows) {
-  return rows >= 128 ? 3 : rows >= 64 ? 2 : rows >= 32 ? 1 : 0;
+  return rows >= 128 ? 3 : rows >= 64 ? 2 : rows >= 32 ? 1 : rows >= 16 ? 0 : 4;
 }
 constexpr int kMaxChunksPerLayer = 6;
 // warps 0-3: weight producer / UMMA issuer / TMEM alloc / ones tile; 4-7, 8-11: epilogue warpgroup of slot 0 / 1.
@@ -68,6 +68,8 @@ struct LayerDesc {
   uint8_t ksteps[kMaxChunksPerLayer];      // UMMA K-steps (of 16) per K-chunk
   uint8_t head_n, has_bias, pad1, pad2;    // EPI_RELU_HEAD: outputs 0..head_n-1; has_bias: bias tile present
   uint32_t bias_off;                       // byte offset of the packed bias tile (N x 32 B, see kBiasTile*)
+  uint32_t cbias_off;                      // byte offset of the COMPACT bias tile (N x 16 B: only the k < 8 core matrices;
+                                           // the inference kernel keeps it outside the weight ring, see kSmemBiasBuf)
   int8_t save_idx;                         // training: slot of this layer's output in save_h / dz_out (-1 none)
   int8_t mask_idx;                         // training fwd: slot of the ReLU bitmask written; bwd: bitmask applied
   uint8_t pad3, pad4;
@@ -82,6 +84,15 @@ struct LayerDesc {
 constexpr int kBiasTileLBO = 128;   // between the two K-adjacent 8x8 core matrices
 constexpr int kBiasTileSBO = 256;   // between N-adjacent core matrices (8-row groups)
 constexpr int kSmemOnes = kSmemMisc + 2816;   // 256-byte ones tile at the end of the misc region
+// Inference kernel: the bias tile of the current layer lives in its own 2 KB buffer instead of occupying a 16 KB stage
+// of the weight ring for the 128 cycles of its UMMA (a ring window that contains a bias stage covers 1150 instead of
+// 1540 cycles of tensor time against a ~1.3 k-cycle refill).  Only k = 0, 1 of a bias tile are non-zero and the "ones"
+// A tile is zero for k >= 2, so the k >= 8 core matrices are dropped: leading-byte-offset 0 aliases them onto the
+// k < 8 ones.  One tile per LAYER serves both slots.
+constexpr int kSmemBiasBuf = kSmemMisc + 512;            // 2 KB: (N/2) rows x 16 B per CTA
+constexpr int kSmemBarBiasFull = kSmemMisc + 256;        // mbarriers of that buffer
+constexpr int kSmemBarBiasEmpty = kSmemMisc + 264;
+constexpr int kCBiasTileSBO = 128;                       // between N-adjacent core matrices of the compact tile
 
 // encodings
 enum : int32_t { ENC_NERF = 0, ENC_FFMLP = 1, ENC_NONE = 2 };
@@ -161,8 +172,9 @@ struct KernelArgs {
   int32_t dz_tma;              // PASS_BWD: 1 = dz_out is written by TMA stores of the bf16 A tile (dz_map)
   int32_t sh_tma;              // PASS_TRAIN_FWD: 1 = save_h is written by TMA stores of the A tile (sh_map)
   // the packed weight arena as rows of 128 bytes, one map per box height (16 / 32 / 64 / 128 rows = the half of a bias
-  // tile or weight K-chunk a CTA stages): 2-SM TMA loads that signal the leader CTA's barrier (ffn_pipeline.cuh)
-  alignas(64) CUtensorMap wmap[4];
+  // tile or weight K-chunk a CTA stages; map 4: 8 rows, half of a 128-wide layer's compact bias tile): 2-SM TMA loads
+  // that signal the leader CTA's barrier (ffn_pipeline.cuh)
+  alignas(64) CUtensorMap wmap[5];
   alignas(64) CUtensorMap dz_map;   // [n_dz][M][256] bf16, boxes of 64 columns x 32 rows, SWIZZLE_128B
   alignas(64) CUtensorMap sh_map;   // [n_save][M][256] operand dtype, same boxes
 };

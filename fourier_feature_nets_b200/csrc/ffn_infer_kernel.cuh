@@ -490,6 +490,8 @@ ffn_infer_kernel(const __grid_constant__ KernelArgs args) {
       ptx::mbar_init(bar_raw_free + 8 * i, 1);
       ptx::mbar_init(bar_drained + 8 * i, 4);
     }
+    ptx::mbar_init(smem_base + kSmemBarBiasFull, 1);      // the leader's producer + the bytes of both CTAs' loads
+    ptx::mbar_init(smem_base + kSmemBarBiasEmpty, 1);     // one multicast commit
     ptx::fence_mbar_init();
   }
   if (warp == 3) {
@@ -525,9 +527,9 @@ ffn_infer_kernel(const __grid_constant__ KernelArgs args) {
   pc.bar_acc_full = bar_acc_full; pc.cta_rank = cta_rank; pc.tmem_base = tmem_base; pc.my_tiles = my_tiles; pc.L = L;
 
   if (warp == 0) {
-    weight_producer(args, pc, lane);
+    weight_producer<true>(args, pc, lane);
   } else if (warp == 1) {
-    if (cta_rank == 0) umma_issuer<kBF16>(args, pc, lane);      // (rank 1's warp 1 idles)
+    if (cta_rank == 0) umma_issuer<kBF16, true>(args, pc, lane);      // (rank 1's warp 1 idles)
   } else if (warp < 4) {
     // ================================================================ aux warp of slot (warp - 2)
     const int slot = warp - 2;

@@ -25,8 +25,11 @@ struct PipeCtx {
   int L;
 };
 
+// kBiasBuf (inference kernel): bias tiles go to their own buffer (kSmemBiasBuf), once per layer for both slots
+template <bool kBiasBuf = false>
 __device__ __forceinline__ void weight_producer(const KernelArgs& args, const PipeCtx& pc, int lane) {
-  uint32_t stage = 0, phase = 0;
+  uint32_t stage = 0, phase = 0, bias_phase = 0;
+  const uint32_t bias_full_leader = ptx::mapa_u32(pc.smem_base + kSmemBarBiasFull, 0u);
   // the leader's (rank 0) "stage full" barriers in shared::cluster space: both CTAs' loads complete_tx there
   uint32_t full_leader[kWStages];
 #pragma unroll
@@ -36,9 +39,21 @@ __device__ __forceinline__ void weight_producer(const KernelArgs& args, const Pi
     for (int l = 0; l < pc.L; ++l) {
       const LayerDesc& ld = args.layers[l];
       const uint32_t bytes = (uint32_t)ld.n * 128u;
+      if (kBiasBuf && ld.has_bias) {
+        // free once the bias UMMA of the previous layer's LAST slot has completed
+        ptx::mbar_wait(pc.smem_base + kSmemBarBiasEmpty, bias_phase ^ 1u);
+        if (lane == 0) {
+          const uint32_t nbytes = (uint32_t)ld.n * 16u, hb = nbytes >> 1;
+          if (pc.cta_rank == 0) ptx::mbar_arrive_expect_tx(pc.smem_base + kSmemBarBiasFull, nbytes);
+          ptx::tma_load_2d_pair(pc.smem_base + kSmemBiasBuf, &args.wmap[wmap_index(hb >> 7)], 0,
+                                (int)((ld.cbias_off + pc.cta_rank * hb) >> 7), bias_full_leader);
+        }
+        __syncwarp();
+        bias_phase ^= 1u;
+      }
       for (int s = 0; s < nslots; ++s) {
-        // chunk -1 = the layer's bias tile (N x 32 B), then the weight K-chunks
-        for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
+        // chunk -1 = the layer's bias tile (N x 32 B) when it travels through the ring, then the weight K-chunks
+        for (int c = (ld.has_bias && !kBiasBuf) ? -1 : 0; c < ld.n_chunks; ++c) {
           ptx::mbar_wait(pc.bar_w_empty + 8 * stage, phase ^ 1u);      // (multicast commit: both CTAs see "stage free")
           if (lane == 0) {
             const uint32_t nbytes = c < 0 ? (uint32_t)ld.n * 32u : bytes;
@@ -61,9 +76,9 @@ __device__ __forceinline__ void weight_producer(const KernelArgs& args, const Pi
   }
 }
 
-template <bool kBF16>
+template <bool kBF16, bool kBiasBuf = false>
 __device__ __forceinline__ void umma_issuer(const KernelArgs& args, const PipeCtx& pc, int lane) {
-  uint32_t stage = 0, phase = 0;
+  uint32_t stage = 0, phase = 0, bias_phase = 0;
   uint32_t a_phase[2] = {0u, 0u};
   const bool prof = args.stats != nullptr;
   long long t_wait_a = 0, t_wait_w = 0, t_begin = prof ? clock64() : 0;
@@ -81,7 +96,25 @@ __device__ __forceinline__ void umma_issuer(const KernelArgs& args, const PipeCt
         const uint32_t slot_base = pc.smem_base + kSmemSlot0 + s * kSlotBytes;
         const uint32_t d_tmem = pc.tmem_base + (uint32_t)s * 256u;
         uint32_t accumulate = ld.accumulate;
-        for (int c = ld.has_bias ? -1 : 0; c < ld.n_chunks; ++c) {
+        if (kBiasBuf && ld.has_bias) {
+          // D = ones(128x16) . bias_tile(Nx16)^T from the dedicated buffer: loaded once per layer, used by both slots
+          if (s == 0) {
+            t0 = prof ? clock64() : 0;
+            ptx::mbar_wait(pc.smem_base + kSmemBarBiasFull, bias_phase);
+            if (prof) t_wait_w += clock64() - t0;
+            ptx::tc_fence_after();
+          }
+          const uint64_t a_desc = ptx::make_kmajor_nosw_desc(pc.smem_base + kSmemOnes, 128u, 0u);
+          const uint64_t b_desc = ptx::make_kmajor_nosw_desc(pc.smem_base + kSmemBiasBuf, 0u, kCBiasTileSBO);
+          ptx::umma_chunk_ss_pair(d_tmem, a_desc, b_desc, idesc, accumulate, 1);
+          if (s == nslots - 1) {      // the buffer may be refilled once this UMMA has read it
+            ptx::umma_commit_warp_pair(pc.smem_base + kSmemBarBiasEmpty, 0u);
+            bias_phase ^= 1u;
+          }
+          accumulate = 1u;
+          __syncwarp();
+        }
+        for (int c = (ld.has_bias && !kBiasBuf) ? -1 : 0; c < ld.n_chunks; ++c) {
           t0 = prof ? clock64() : 0;
           // completes on the bytes of both halves (mine and the peer's: 2-SM TMA loads signal this barrier); the
           // operands themselves are read through the async proxy, so a CTA-scope wait is enough
