@@ -175,16 +175,17 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs pa, const i
   }
 }
 
-// bias tiles (B operand of the bias UMMA, layout in ffn_common.cuh) + head weights in ConstParams
+// bias tiles (B operand of the bias UMMA, layout in ffn_common.cuh) + head weights in ConstParams.
+// One block per MMA layer (its bias) and one per output-head row: every block does one short pass.
 template <bool kBF16>
 __global__ void pack_const_kernel(const __grid_constant__ PackArgs pa, ConstParams* __restrict__ cp,
                                   uint8_t* __restrict__ wpack) {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nth = gridDim.x * blockDim.x;
-  for (int l = 0; l < pa.n_layers; ++l) {
-    if (pa.bias_row[l] < 0) continue;
+  const int blk = blockIdx.x;
+  if (blk < pa.n_layers) {
+    const int l = blk;
+    if (pa.bias_row[l] < 0) return;
     const float* b = pa.b[pa.linear[l]];
-    for (int n = tid; n < pa.n[l]; n += nth) {
+    for (int n = threadIdx.x; n < pa.n[l]; n += blockDim.x) {
       const float v = b[n];
       float hi;
       if constexpr (kBF16) hi = __bfloat162float(__float2bfloat16_rn(v));
@@ -196,16 +197,20 @@ __global__ void pack_const_kernel(const __grid_constant__ PackArgs pa, ConstPara
       *reinterpret_cast<uint32_t*>(wpack + pa.cbias_off[l] + (size_t)(n >> 3) * kCBiasTileSBO +
                                    (size_t)(n & 7) * 16) = pk;
     }
+    return;
   }
+  int row = blk - pa.n_layers;      // output-head row (0 .. sum of head_n)
   for (int h = 0; h < pa.n_heads; ++h) {
-    const float* w = pa.w[pa.head_linear[h]];
-    const float* b = pa.b[pa.head_linear[h]];
-    const int inf = pa.head_in[h];
-    for (int o = 0; o < pa.head_n[h]; ++o) {
-      for (int i = tid; i < 256; i += nth)
+    if (row < pa.head_n[h]) {
+      const float* w = pa.w[pa.head_linear[h]];
+      const float* b = pa.b[pa.head_linear[h]];
+      const int inf = pa.head_in[h], o = row;
+      for (int i = threadIdx.x; i < 256; i += blockDim.x)
         cp->head_w[pa.head_first[h] + o][i] = i < inf ? w[(size_t)o * inf + i] : 0.f;
-      if (tid == 0) cp->head_b[pa.head_first[h] + o] = b[o];
+      if (threadIdx.x == 0) cp->head_b[pa.head_first[h] + o] = b[o];
+      return;
     }
+    row -= pa.head_n[h];
   }
 }
 
@@ -652,8 +657,10 @@ extern "C" int ffn_net_pack(ffn_net_t* net, const float* const* weights, const f
   dim3 grid(40, net->num_layers);
   if (net->bf16) pack_weights_kernel<true><<<grid, 256, 0, stream>>>(pa, net->d_colmap, net->d_wpack);
   else pack_weights_kernel<false><<<grid, 256, 0, stream>>>(pa, net->d_colmap, net->d_wpack);
-  if (net->bf16) pack_const_kernel<true><<<16, 256, 0, stream>>>(pa, net->d_cparams, net->d_wpack);
-  else pack_const_kernel<false><<<16, 256, 0, stream>>>(pa, net->d_cparams, net->d_wpack);
+  int head_rows = 0;
+  for (int h = 0; h < pa.n_heads; ++h) head_rows += pa.head_n[h];
+  if (net->bf16) pack_const_kernel<true><<<pa.n_layers + head_rows, 256, 0, stream>>>(pa, net->d_cparams, net->d_wpack);
+  else pack_const_kernel<false><<<pa.n_layers + head_rows, 256, 0, stream>>>(pa, net->d_cparams, net->d_wpack);
   g_launches += 2;
   if (net->precise) {
     pack_weights_kernel<false, true><<<grid, 256, 0, stream>>>(pa, net->d_colmap, net->d_wpack + net->wpack_bytes);
@@ -691,7 +698,10 @@ static int launch_variant(const cudaLaunchConfig_t& cfg, const KernelArgs& ka) {
   return 0;
 }
 
-static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int pass = PASS_INFER) {
+// sigma_only (coarse pass of hierarchical sampling, ray_sampler.py:234-269: only model(...)[:, -1] is used): NeRF handles
+// run the trunk alone -- opacity_out reads the last trunk layer (nerf_model.py:117-118) -- and leave rgb at 0
+static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int pass = PASS_INFER,
+                         bool sigma_only = false) {
   if (!net->packed) return fail("net has no packed weights: call ffn_net_pack first");
   if (ka.M <= 0) return 0;
   if (g_loaded_gen != net->gen) {
@@ -709,7 +719,11 @@ static int launch_render(ffn_net* net, KernelArgs& ka, cudaStream_t stream, int 
     ka.wpack_lo_off = (uint32_t)net->wpack_bytes;
     static const bool env_nofold = getenv("FFN_FOLD") != nullptr && atoi(getenv("FFN_FOLD")) == 0;
     const bool folded = pass == PASS_INFER && !net->precise && ka.dbg_layer < 0 && net->num_layers_inf > 0 && !env_nofold;
-    if (folded) {
+    if (sigma_only && pass == PASS_INFER && net->kind == ENC_NERF && !net->precise && !ka.fused && ka.dbg_layer < 0 &&
+        !env_nofold) {
+      memcpy(ka.layers, net->layers, sizeof(net->layers));
+      ka.num_layers = net->num_linear - 4;      // trunk only; its last layer carries the opacity head
+    } else if (folded) {
       if (net->fold_gen != net->gen) {      // weights changed since the folded image was built
         const int L = net->num_linear - 4;
         const int threads = 256, blocks = (kFoldedN * 320 + threads - 1) / threads;

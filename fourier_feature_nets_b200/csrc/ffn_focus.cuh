@@ -167,7 +167,7 @@ extern "C" int ffn_focus_sample(ffn_net_t* coarse, const float* starts, const fl
   memset(&ka, 0, sizeof(ka));
   ka.mode = MODE_RAYS; ka.org = starts; ka.dir = directions; ka.near_ = near_; ka.far_ = far_; ka.lin = lin_c;
   ka.stratified = 0; ka.M = Mc; ka.S = S_c; ka.fused = 0; ka.dbg_layer = -1; ka.raw = coarse->d_scratch;
-  if (launch_render(coarse, ka, stream)) return 1;
+  if (launch_render(coarse, ka, stream, PASS_INFER, /*sigma_only=*/true)) return 1;
   return ffn_focus_t(coarse->d_scratch, 4, near_, far_, near_u, far_u, lin_c, lin_u, lin_f, jitter_u, u_focus,
                      stratified, seed, ray_offset, R, S, t_out, stream_);
 }

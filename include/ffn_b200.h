@@ -85,7 +85,12 @@ void ffn_net_destroy(ffn_net_t* net);
 int ffn_net_num_linear(const ffn_net_t* net);
 
 /* Re-pack torch-layout (out,in) float32 weights + biases (device pointers, given as HOST
- * arrays of pointers) into the tensor-core layout.  Call after every optimiser step. */
+ * arrays of pointers) into the tensor-core layout.  Call after every optimiser step.
+ * NeRF handles remember the pointers: the first INFERENCE launch after a pack reads bottleneck / hidden_view once
+ * more (stream-ordered, one small launch) to build the folded layer its program runs (bottleneck has no activation,
+ * nerf_model.py:119-122, so bottleneck . hidden_view is one 128-wide layer).  The parameters must therefore stay
+ * allocated, and unchanged unless ffn_net_pack is called again, until that launch -- true for a model's own
+ * nn.Parameter storage.  FFN_FOLD=0 in the environment keeps the reference's layer structure. */
 int ffn_net_pack(ffn_net_t* net, const float* const* weights, const float* const* biases,
                  void* stream);
 

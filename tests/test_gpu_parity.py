@@ -434,3 +434,50 @@ def test_fp16x3_precise_mode_matches_fp32(golden_nerf):
     assert np.abs(c.cpu().numpy() - ref.color).max() <= 5e-5
     assert np.abs(a.cpu().numpy() - ref.alpha).max() <= 5e-5
     assert (dep.cpu().numpy() != ref.depth).mean() <= 1e-3
+
+
+_FOLD_PROBE = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+import fourier_feature_nets_b200 as ffn
+g = np.load(sys.argv[2])
+m = ffn.NeRF(8, 256, 9, 10, 3, 4, [4], True)
+m.load_state_dict({k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w.")})
+m = m.to("cuda:0").eval()
+with torch.no_grad():
+    p = torch.from_numpy(g["positions"]).to("cuda:0").reshape(-1, 3)
+    v = torch.from_numpy(g["view_directions"]).to("cuda:0").reshape(-1, 3)
+    raw = m(p, v)
+    # the weights change: the folded layer must follow (it is rebuilt lazily by the next render)
+    m.bottleneck.weight.mul_(0.5)          # (in-place on the parameter: bumps its version counter -> re-pack)
+    m.hidden_view.bias.add_(0.25)
+    raw2 = m(p, v)
+np.savez(sys.argv[3], raw=raw.cpu().numpy(), raw2=raw2.cpu().numpy())
+"""
+
+
+def test_folded_inference_program_equals_the_reference_layer_structure(tmp_path):
+    """The inference kernel runs bottleneck . hidden_view as ONE folded layer (nerf_model.py:119-122 has no activation
+    in between).  FFN_FOLD=0 runs the reference's two layers through the same kernel: raw outputs of the
+    two programs agree to operand rounding, before and after a weight update (the folded image is rebuilt)."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    script = tmp_path / "probe.py"
+    script.write_text(_FOLD_PROBE)
+    outs = {}
+    for fold in ("1", "0"):
+        out = tmp_path / ("fold%s.npz" % fold)
+        env = dict(os.environ, FFN_FOLD=fold)
+        res = subprocess.run([sys.executable, str(script), ROOT, os.path.join(GOLDEN, "nerf_render.npz"), str(out)],
+                             env=env, capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stderr[-2000:]
+        outs[fold] = np.load(out)
+    g = load("nerf_render.npz")
+    scale = float(np.abs(g["raw"]).max())
+    for key in ("raw", "raw2"):
+        a, b = outs["1"][key], outs["0"][key]
+        assert np.isfinite(a).all() and np.abs(a - b).max() <= 4e-3 * scale, (key, np.abs(a - b).max(), scale)
+    # both follow the reference's fp32 outputs, and the update really changed them
+    assert np.abs(outs["1"]["raw"].reshape(g["raw"].shape) - g["raw"]).max() <= 4e-3 * scale
+    assert np.abs(outs["1"]["raw2"] - outs["1"]["raw"]).max() > 1e-2
