@@ -341,6 +341,10 @@ def main():
 
     # ---- end to end through the public API with HOST buffers: host ray tables -> RaySampler.sample (gather into
     # pinned staging) -> H2D -> Raycaster.render -> D2H; everything inside the timed region ---------------------------
+    # torchrun exports OMP_NUM_THREADS=1: the host-side gather of RaySampler.sample (torch.index_select over the host ray
+    # tables) would run on ONE core per rank and bound the e2e number at N > 1; give every rank its share of the cores
+    host_threads = max(1, host_cores() // world)
+    torch.set_num_threads(host_threads)
     host_sampler = ffn.RaySampler.__new__(ffn.RaySampler)
     host_sampler.__dict__.update(sampler.__dict__)
     host_sampler.to("cpu")
@@ -407,6 +411,7 @@ def main():
                     "api": "Raycaster.render_stream(sampler, index_batches, True): host ray tables -> RaySampler.sample "
                            "(gather into pinned staging) -> H2D -> fused kernel -> D2H -> numpy, every stage inside the "
                            "timed region, host work of step i+1 overlapped with the kernel of step i",
+                    "host_threads_per_rank": host_threads,
                     "serial_value": world * R * K / (e2e_serial_ms / 1e3),
                     "device_tables_value": world * R * K / (e2e_dev_ms / 1e3)},
             "gpu_launches": int(launches),
