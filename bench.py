@@ -436,7 +436,7 @@ def main():
 
     # ---- training step: FusedTrainer, 128 samples/ray; at N > 1 with the NCCL
     # all-reduce of the 595,844 gradients between backward and update (mean folded into ffn_clip_adam) ----------------
-    def train_leg(rays_per_rank, label, steps=40, warm=8, S=128):
+    def train_leg(rays_per_rank, label, steps=120, warm=12, S=128):
         torch.manual_seed(20080524)
         if label == "tiny":       # configs[1]: train_tiny_nerf.py positional preset (train_tiny_nerf.py:75-88)
             tm = ffn.PositionalFourierMLP(3, 4, 5.5).to(dev)

@@ -437,9 +437,14 @@ __device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, ui
 
 // TMA tensor store shared -> global (3-D map), bulk async-group completion
 __device__ __forceinline__ void tma_store_3d(const void* map, uint32_t src_smem, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
-               ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(src_smem)
-               : "memory");
+  // the saves are written once and read once, a whole kernel later and long after they have left the L2:
+  // evict-first keeps them from displacing the weight stream
+  asm volatile(
+      "{\n\t.reg .b64 pol;\n\t"
+      "createpolicy.fractional.L2::evict_first.b64 pol, 1.0;\n\t"
+      "cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], pol;\n\t}"
+      ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(src_smem)
+      : "memory");
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all bulk groups of this thread have finished READING their shared-memory source
