@@ -30,6 +30,7 @@ template <bool kBiasBuf = false>
 __device__ __forceinline__ void weight_producer(const KernelArgs& args, const PipeCtx& pc, int lane) {
   uint32_t stage = 0, phase = 0, bias_phase = 0;
   const uint32_t bias_full_leader = ptx::mapa_u32(pc.smem_base + kSmemBarBiasFull, 0u);
+  const uint64_t keep = kBiasBuf ? 0ull : ptx::l2_policy_evict_last();     // (training passes, see tma_load_2d_pair_hint)
   // the leader's (rank 0) "stage full" barriers in shared::cluster space: both CTAs' loads complete_tx there
   uint32_t full_leader[kWStages];
 #pragma unroll
@@ -65,8 +66,12 @@ __device__ __forceinline__ void weight_producer(const KernelArgs& args, const Pi
             const uint32_t rows = hb >> 7;
             const int mi = wmap_index(rows);
             if (pc.cta_rank == 0) ptx::mbar_arrive_expect_tx(pc.bar_w_full + 8 * stage, nbytes);
-            ptx::tma_load_2d_pair(pc.smem_base + kSmemW + stage * kWStageBytes, &args.wmap[mi], 0,
-                                  (int)((src_off + pc.cta_rank * hb) >> 7), full_leader[stage]);
+            if constexpr (kBiasBuf)
+              ptx::tma_load_2d_pair(pc.smem_base + kSmemW + stage * kWStageBytes, &args.wmap[mi], 0,
+                                    (int)((src_off + pc.cta_rank * hb) >> 7), full_leader[stage]);
+            else
+              ptx::tma_load_2d_pair_hint(pc.smem_base + kSmemW + stage * kWStageBytes, &args.wmap[mi], 0,
+                                         (int)((src_off + pc.cta_rank * hb) >> 7), full_leader[stage], keep);
           }
           __syncwarp();
           if (++stage == kWStages) { stage = 0; phase ^= 1u; }

@@ -95,6 +95,22 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const void* 
       ::"r"(dst_smem), "l"(map), "r"(c0), "r"(c1), "r"(mbar)
       : "memory");
 }
+// the same with an L2 cache policy (training passes: the 1.2 MB weight arena is re-read by every cluster for every tile
+// pair while 0.6 GB of saves stream through the L2 -- evict-last keeps it resident).  The policy is created ONCE per
+// kernel: a createpolicy in front of every load sits on the ring's refill chain (-8 % in the inference kernel).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(uint32_t dst_smem, const void* map, int c0, int c1, uint32_t mbar,
+                                                      uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst_smem), "l"(map), "r"(c0), "r"(c1), "r"(mbar), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
@@ -430,7 +446,7 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 // sectors instead of two half sectors in two instructions
 __device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
                                              uint32_t f, uint32_t g, uint32_t h) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d),
+  asm volatile("st.global.L2::evict_first.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d),
                "r"(e), "r"(f), "r"(g), "r"(h)
                : "memory");
 }
