@@ -186,10 +186,17 @@ __device__ __forceinline__ void save_data_global(const uint32_t (&v)[32], void* 
 }
 // sign word of an accumulator block: bit (31-j) = 1 <=> column j is negative, i.e. ReLU'(.) = 0
 __device__ __forceinline__ uint32_t sign_word(const uint32_t (&v)[32]) {
-  uint32_t w = 0;
+  // four independent funnel-shift chains of 8 (one chain of 32 dependent shifts costs ~160 cycles of latency per block,
+  // 1.3 k cycles per 256-wide layer on the epilogue chain), then one merge
+  uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) w = __funnelshift_l(v[j], w, 1);
-  return w;
+  for (int j = 0; j < 8; ++j) {
+    w0 = __funnelshift_l(v[j], w0, 1);
+    w1 = __funnelshift_l(v[8 + j], w1, 1);
+    w2 = __funnelshift_l(v[16 + j], w2, 1);
+    w3 = __funnelshift_l(v[24 + j], w3, 1);
+  }
+  return (w0 << 24) | (w1 << 16) | (w2 << 8) | w3;
 }
 
 // backward: zero the columns whose forward pre-activation was negative (sign word from the forward)
