@@ -201,3 +201,25 @@ def test_torch_oracle_sampling_and_agreement_with_the_numpy_oracle():
     np.testing.assert_allclose(got.color.numpy(), want.color, rtol=0, atol=3e-5)
     np.testing.assert_allclose(got.alpha.numpy(), want.alpha, rtol=0, atol=3e-5)
     assert g is not None
+
+
+def test_bottleneck_hidden_view_fold_identity():
+    """The identity the inference kernel's folded program rests on (nerf_model.py:119-122 has no activation
+    between ``bottleneck`` and ``hidden_view``):  hidden_view([bottleneck(h) | enc_v])
+    = (W_hv[:, :256] W_b) h + W_hv[:, 256:] enc_v + (W_hv[:, :256] b_b + b_hv).  Checked in fp64 on the reference's own
+    golden network: the raw outputs of the folded network equal the reference's recorded fp64 outputs."""
+    g = np.load(os.path.join(GOLDEN, "nerf_render.npz"))
+    p = {k[2:]: g[k].astype(np.float64) for k in g.files if k.startswith("w.")}
+    pos = g["positions"].reshape(-1, 3).astype(np.float64)
+    view = g["view_directions"].reshape(-1, 3).astype(np.float64)
+    ref = oracle.nerf_forward(p, pos, view)
+    assert np.abs(ref - g["raw64"]).max() <= 1e-9 * max(1.0, np.abs(g["raw64"]).max())
+    w_hv, w_b = p["hidden_view.weight"], p["bottleneck.weight"]
+    folded = dict(p)
+    # a "bottleneck" that is the identity and a hidden_view that carries the product: same graph, folded weights
+    folded["bottleneck.weight"] = np.eye(256)
+    folded["bottleneck.bias"] = np.zeros(256)
+    folded["hidden_view.weight"] = np.concatenate([w_hv[:, :256] @ w_b, w_hv[:, 256:]], axis=1)
+    folded["hidden_view.bias"] = w_hv[:, :256] @ p["bottleneck.bias"] + p["hidden_view.bias"]
+    out = oracle.nerf_forward(folded, pos, view)
+    assert np.abs(out - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max())
